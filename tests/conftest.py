@@ -1,0 +1,34 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def split_params(npz, prefix):
+    """'p/model_coarse.linear_x.0.weight' -> {'coarse': {...}, 'fine': {...}}"""
+    out = {'coarse': {}, 'fine': {}}
+    for k in npz.files:
+        if k.startswith(prefix + '/'):
+            name = k[len(prefix) + 1:]
+            net, rest = name.split('.', 1)
+            out[net.replace('model_', '')][rest] = npz[k]
+    return out
+
+
+@pytest.fixture(scope='session')
+def golden():
+    return load_golden

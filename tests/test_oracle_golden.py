@@ -1,0 +1,186 @@
+"""Pins oracle/nerf_oracle.py against vectors produced by the unmodified reference
+(oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, split_params
+from oracle import nerf_oracle as orc
+
+
+def ulp_diff(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b, dtype=np.float32).view(np.int32).astype(np.int64)
+    return np.abs(a - b)
+
+
+def test_make_o_d_bit_exact():
+    g = load_golden('raygen.npz')
+    o, d = orc.make_o_d(int(g['W']), int(g['H']), g['K'], g['pose'])
+    assert np.array_equal(o, g['rays_o'])
+    assert np.array_equal(d, g['rays_d'])          # bit-exact: fma chain
+    o8, d8 = orc.make_o_d(int(g['W8']), int(g['H8']), g['K8'], g['pose8'])
+    sel = g['sel8']
+    assert np.array_equal(o8.reshape(-1, 3)[sel], g['rays_o8'])
+    assert np.array_equal(d8.reshape(-1, 3)[sel], g['rays_d8'])
+
+
+def test_get_rays_np():
+    g = load_golden('raygen.npz')
+    o, d = orc.get_rays_np(int(g['H']), int(g['W']), g['K'], g['pose'])
+    if str(g['np_dtype']) == str(d.dtype):
+        assert np.array_equal(d, g['np_rays_d'])
+    else:  # fixture made under another NumPy major version (SURVEY B-3)
+        np.testing.assert_allclose(d, g['np_rays_d'], rtol=1e-6)
+    assert np.array_equal(np.ascontiguousarray(o), g['np_rays_o'])
+
+
+def test_ndc_rays_bit_exact():
+    g = load_golden('ndc.npz')
+    o, d = orc.ndc_rays(int(g['H']), int(g['W']), float(g['focal']), 1., g['rays_o'], g['rays_d'])
+    assert np.array_equal(o, g['ndc_o'])
+    assert np.array_equal(d, g['ndc_d'])
+
+
+def test_positional_encoding():
+    g = load_golden('posenc.npz')
+    ex = orc.positional_encoding(g['x'], 10)
+    ed = orc.positional_encoding(g['d'], 4)
+    assert ex.shape[1] == int(g['out_dim_x']) == 63 and ed.shape[1] == int(g['out_dim_d']) == 27
+    # identity block and argument products are exact; sin/cos differ by libm ulps only
+    assert np.array_equal(ex[:, :3], g['enc_x'][:, :3])
+    assert np.abs(ex - g['enc_x']).max() <= 5e-7
+    assert np.abs(ed - g['enc_d']).max() <= 5e-7
+
+
+def test_torch_linspace():
+    g = load_golden('pre_process_coarse.npz')
+    assert np.array_equal(orc.torch_linspace01(64), g['t_vals'])
+    assert np.array_equal(orc.torch_linspace01(128), g['t_vals_128'])
+    assert np.array_equal(orc.torch_linspace01(192), g['t_vals_192'])
+
+
+def test_pre_process_coarse():
+    g = load_golden('pre_process_coarse.npz')
+    z = orc.stratified_z(float(g['near']), float(g['far']), 64, g['t_rand'])
+    assert np.array_equal(z, g['z_vals'])          # bit-exact: individually rounded ops
+    emb = orc.embed_points(g['rays'], z)
+    assert emb.shape == g['embedded'].shape
+    # PE arguments reach 2^9*|x| so an ulp of the point (norm/sum order) moves sin/cos by ~1e-4 at the top band
+    assert np.abs(emb[:, :3] - g['embedded'][:, :3]).max() <= 1e-6
+    assert np.abs(emb - g['embedded']).max() <= 2e-3
+    assert np.abs(emb[:, :33] - g['embedded'][:, :33]).max() <= 5e-5
+
+
+def test_sample_pdf_from_reference_cdf_bit_exact():
+    """Given the reference's own cdf the inverse-CDF stage is bit-exact (indices AND samples)."""
+    g = load_golden('sample_pdf.npz')
+    for tag in ('det', 'rnd'):
+        u = g[f'u_{tag}']
+        u = np.broadcast_to(u, (g['cdf'].shape[0], u.shape[-1]))
+        s, inds = orc.invert_cdf(g['bins'], g['cdf'], u)
+        assert np.array_equal(inds, g[f'inds_{tag}'])
+        assert np.array_equal(s, g[f'samples_{tag}'])
+
+
+def test_sample_pdf_own_cdf():
+    """With the oracle's own (fp64-accumulated) cdf, indices can differ from the reference's
+    device-specific summation order only at knot ties (SURVEY B-5)."""
+    g = load_golden('sample_pdf.npz')
+    cdf = orc.pdf_to_cdf(g['weights'][..., 1:-1])
+    assert ulp_diff(cdf, g['cdf']).max() <= 4
+    for tag in ('det', 'rnd'):
+        s, inds = orc.sample_pdf(g['bins'], g['weights'][..., 1:-1], g[f'u_{tag}'])
+        mism = inds != g[f'inds_{tag}']
+        assert mism.mean() < 2e-3, mism.mean()
+        assert np.abs(inds - g[f'inds_{tag}']).max() <= 1
+        # same bin -> same sample up to the ulp of the cdf; at a flipped tie the sample may jump by at
+        # most one bin (flat-pdf bins use denom=1, nerf_process.py:179, so the inverse CDF is not continuous)
+        # conditioning: d(sample) <= ulp(cdf)/denom * bin_width with denom >= 1e-5 (nerf_process.py:179)
+        err = np.abs(s - g[f'samples_{tag}'])[~mism]
+        assert err.max() <= 2e-3 and np.quantile(err, 0.999) <= 2e-5
+        width = np.diff(g['bins'], axis=-1).max()
+        assert np.abs(s - g[f'samples_{tag}']).max() <= width
+
+
+def test_fine_z_and_embedding():
+    g = load_golden('sample_pdf.npz')
+    z_f, _, _ = orc.fine_z(g['fine_z_in'], g['fine_w_in'], g['fine_u'])
+    assert z_f.shape == g['fine_z'].shape == (8, 192)
+    assert np.abs(z_f - g['fine_z']).max() <= 2e-5
+    assert np.all(np.diff(z_f, axis=-1) >= 0)
+
+
+@pytest.mark.parametrize('S', [64, 192])
+def test_post_process(S):
+    g = load_golden(f'post_process_S{S}.npz')
+    rgb, disp, acc, w, depth = orc.post_process(g['raw'], g['z_vals'], g['rays_d'])
+    assert np.abs(w - g['weights']).max() <= 5e-6   # exp() libm ulps x weights<=1
+    assert np.abs(rgb - g['rgb_map']).max() <= 1e-5
+    assert np.abs(acc - g['acc_map']).max() <= 1e-5
+    assert np.abs(depth - g['depth_map']).max() <= 1e-4
+    assert np.abs(disp - g['disp_map']).max() <= 1e-4
+    # edge cases (SURVEY B-8): empty rays -> disp 0, acc 0, white background
+    assert np.all(disp[:8] == 0) and np.all(acc[:8] == 0) and np.all(rgb[:8] == 1)
+    assert np.all(disp[32:40] <= 5.0)
+    d_raw = orc.post_process_backward(g['raw'], g['z_vals'], g['rays_d'], g['d_rgb'])
+    scale = np.abs(g['d_raw']).max()
+    assert np.abs(d_raw - g['d_raw']).max() <= 1e-4 * max(scale, 1.)
+
+
+def test_mlp_w64_forward_backward():
+    g = load_golden('mlp_w64.npz')
+    p = split_params(g, 'p')
+    yc = orc.mlp_forward(p['coarse'], g['x'])
+    yf = orc.mlp_forward(p['fine'], g['x'])
+    assert np.abs(yc - g['y_coarse']).max() <= 1e-5
+    assert np.abs(yf - g['y_fine']).max() <= 1e-5
+    grads = orc.mlp_backward(p['coarse'], g['x'], g['d_y'])
+    for k in grads:
+        ref = g['g/' + k]
+        assert grads[k].shape == ref.shape
+        assert np.abs(grads[k] - ref).max() <= 1e-4 * max(1., np.abs(ref).max()), k
+
+
+def test_render_and_train_w64():
+    g = load_golden('render_train_w64.npz')
+    p = split_params(g, 'p')
+    opts = orc.make_opts(near=float(g['near']), far=float(g['far']))
+    rays = np.concatenate([g['rays_o'], g['rays_d']], -1)
+    r = orc.render_rays(rays, p['coarse'], p['fine'], opts, g['t_rand'], g['u'])
+    for k in ('rgb_c', 'rgb_f'):
+        assert np.abs(r[k] - g[k]).max() <= 1e-4, k
+    for k in ('disp_c', 'disp_f'):
+        assert np.abs(r[k] - g[k]).max() <= 1e-3, k
+    lc, lf, gc, gf = orc.train_grads(rays, g['target'], p['coarse'], p['fine'], opts, g['t_rand'], g['u'])
+    assert abs(lc - float(g['loss_c'])) <= 1e-5 and abs(lf - float(g['loss_f'])) <= 1e-5
+    for tag, grads in (('coarse', gc), ('fine', gf)):
+        num = den = 0.
+        for k, v in grads.items():
+            ref = g[f'g/model_{tag}.{k}']
+            num += float(((v - ref).astype(np.float64) ** 2).sum())
+            den += float((ref.astype(np.float64) ** 2).sum())
+        assert np.sqrt(num / den) <= 1e-3, (tag, np.sqrt(num / den))
+    # one Adam step (main.py:79-80)
+    a = split_params(g, 'a')
+    for tag, grads in (('coarse', gc), ('fine', gf)):
+        for k, v in grads.items():
+            ref_g = g[f'g/model_{tag}.{k}']
+            newp, _, _ = orc.adam_step(p[tag][k], ref_g, np.zeros_like(ref_g), np.zeros_like(ref_g), 1, float(g['lr']))
+            assert np.abs(newp - a[tag][k]).max() <= 1e-6, k
+
+
+def test_render_llff_w64():
+    g = load_golden('render_llff_w64.npz')
+    a = split_params(g, 'a')
+    opts = orc.make_opts(near=0., far=1., data_type='llff', perturb=0.)
+    r = orc.render(g['rays_o'], g['rays_d'], a['coarse'], a['fine'], opts, g['t_rand'], g['u_det'],
+                   H=int(g['H']), W=int(g['W']), focal=float(g['focal']))
+    for k in ('rgb_c', 'rgb_f'):
+        assert np.abs(r[k] - g[k]).max() <= 1e-4, k
+
+
+def test_lr_schedule():
+    assert abs(orc.lr_at(0) - 5e-5) < 1e-12
+    assert abs(orc.lr_at(10000) - 5e-4) < 1e-12
+    assert abs(orc.lr_at(5000) - (5e-5 + 4.5e-4 * 0.5)) < 1e-12
+    assert orc.lr_at(200000) < 5.1e-5
