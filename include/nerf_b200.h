@@ -1,0 +1,180 @@
+/*
+ * nerf_b200.h -- C ABI of libnerf_b200.so, the B200 (sm_100a) engine behind the
+ * ray-batch hot path of nuggy875/NeRF_pytorch_paeng.
+ *
+ * The reference has no FFI of its own: its "plugin boundary" is the Python call
+ * surface of rays.py / nerf_process.py / model/*.py.  Every
+ * entry point below names the reference interface (file:line under the
+ * reference tree) whose body it replaces; nerf_pytorch_paeng_b200/ holds the
+ * Python mirror of those interfaces, which binds this library with ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch types.
+ *  - All data pointers are DEVICE pointers on the handle's GPU unless a
+ *    parameter is documented as "host".  Tensors are contiguous row-major
+ *    fp32 unless stated; index tensors are int64.
+ *  - Every call returns 0 (NB_OK) or a negative nb_status; the text of the
+ *    last error of a handle is nb_last_error(h).  Nothing throws.
+ *  - No call allocates or frees caller-visible memory and no call
+ *    synchronises the device: work is enqueued on `stream` (a cudaStream_t
+ *    passed as void*; NULL = legacy default stream).  Scratch memory comes
+ *    from a caller-supplied workspace whose size is queried first.
+ *  - One handle per GPU per process; calls on one handle are not re-entrant.
+ *  - There is no CPU fallback: without a CUDA device nb_create fails.
+ */
+#ifndef NERF_B200_H_
+#define NERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; only this ABI is exported */
+#endif
+
+#define NB_ABI_VERSION 1
+
+typedef struct nb_handle_s* nb_handle_t;
+
+typedef enum {
+  NB_OK = 0,
+  NB_ERR_INVALID = -1,    /* bad argument (shape, NULL pointer, unsupported size) */
+  NB_ERR_CUDA = -2,       /* a CUDA runtime call failed; see nb_last_error */
+  NB_ERR_WORKSPACE = -3,  /* workspace too small */
+  NB_ERR_UNSUPPORTED = -4 /* valid request this build cannot serve (e.g. not sm_100) */
+} nb_status;
+
+typedef enum {
+  NB_FP32 = 0, /* CUDA-core FFMA path: the <=1e-4 parity path */
+  NB_BF16 = 1  /* tcgen05 tensor-core path: bf16 operands, fp32 accumulate in TMEM */
+} nb_precision;
+
+/* Topology of one NeRFModule (model/NeRF.py:10-30): D trunk layers of width W,
+ * input_ch = in_x (63), input_ch_d = in_d (27), a single skip layer index
+ * (skips=[4]) after which the trunk input becomes [x, h] (NeRF.py:40-41).
+ * Parameters travel as ONE flat fp32 buffer in model.parameters() order:
+ *   linear_x.0.weight [W,in_x], linear_x.0.bias [W], ... linear_x.{D-1}.*,
+ *   linear_d.weight [W/2, W+in_d], linear_d.bias, linear_feat.weight [W,W], .bias,
+ *   linear_density.weight [1,W], .bias, linear_color.weight [3,W/2], .bias
+ * (nn.Linear layout weight[out,in]).  Gradients use the same layout. */
+typedef struct {
+  int32_t D;     /* 8   */
+  int32_t W;     /* 256 (multiple of 64) */
+  int32_t in_x;  /* 63 = 3 + 6*L_x */
+  int32_t in_d;  /* 27 = 3 + 6*L_d */
+  int32_t skip;  /* 4, or -1 for none */
+  int32_t L_x;   /* 10 */
+  int32_t L_d;   /* 4  */
+} nb_mlp_desc;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int nb_abi_version(void);
+/* device: CUDA ordinal.  flags: reserved, 0.  Fails with NB_ERR_CUDA if there is no GPU and
+ * NB_ERR_UNSUPPORTED if the GPU is not compute capability 10.x. */
+int nb_create(nb_handle_t* out, int device, unsigned flags);
+int nb_destroy(nb_handle_t h);
+const char* nb_last_error(nb_handle_t h);
+/* info[0]=SM count, [1]=cc major, [2]=cc minor, [3]=kernels launched by this handle so far (low 31 bits) */
+int nb_device_info(nb_handle_t h, int32_t info[4]);
+int64_t nb_launch_count(nb_handle_t h);
+
+/* ---- K1: ray generation ---------------------------------------------------------------- */
+/* rays.py:20-34 make_o_d (+ rays.py:59-60 gather when pix_idx != NULL, + nerf_process.py:8-28
+ * when NB_RAYGEN_NDC).  pose: 3x4 row-major c2w with `pose_ld` floats between rows.
+ * pix_idx: N flat pixel indices r*W+c, or NULL for the full image (then N must be H*W).
+ * Arithmetic: x=(c-cx)/fx, y=-((r-cy)/fy) individually rounded, K demoted to fp32;
+ * d_k = fma(-1,R[k][2], fma(y,R[k][1], x*R[k][0])) (the order MKL/cuBLAS K=3 produces). */
+#define NB_RAYGEN_NDC 1u
+int nb_raygen_pinhole(nb_handle_t h, int32_t H, int32_t W, double fx, double fy, double cx, double cy,
+                      const float* pose, int64_t pose_ld, const int64_t* pix_idx, int64_t N,
+                      float* rays_o, float* rays_d, unsigned flags, double ndc_focal, double ndc_near,
+                      void* stream);
+/* nerf_process.py:8-28 ndc_rays on arbitrary rays [N,3] (the global-batch path). In-place allowed. */
+int nb_ndc_rays(nb_handle_t h, int64_t N, int32_t H, int32_t W, double focal, double near,
+                const float* rays_o, const float* rays_d, float* o_out, float* d_out, void* stream);
+/* rays.py:62 target gather: out[n,:] = img[pix_idx[n],:], img is [H*W,C] fp32. */
+int nb_gather_rows(nb_handle_t h, int64_t N, int32_t C, const int64_t* idx, const float* src, float* out,
+                   void* stream);
+
+/* ---- K2: sampling ---------------------------------------------------------------------- */
+/* nerf_process.py:43-60: z[n,s] = lower[s] + span[s]*t_rand[n,s]  (span = upper-lower, both [S_c],
+ * computed once by the caller from torch.linspace).  t_rand NULL => in-kernel Philox4x32-10
+ * keyed by (seed, offset). */
+int nb_stratified(nb_handle_t h, int64_t N, int32_t S_c, const float* lower, const float* span,
+                  const float* t_rand, uint64_t seed, uint64_t offset, float* z_out, void* stream);
+/* nerf_process.py:62-67 + 144-182: mids, pdf, cdf, inverse-CDF sampling, merge with z_c, sort.
+ * u_mode 0: u is [S_f] shared by all rays (det=True: torch.linspace); 1: u is [N,S_f] (injected
+ * torch.rand); 2: u NULL, Philox(seed, offset).  cdf_in (optional, [N,S_c-1]) overrides the
+ * kernel's own cdf (parity tests against a reference cdf).  bins_in (optional, [N,S_c-1]) gives the
+ * bin positions directly instead of mids(z_c) (the stand-alone sample_pdf(bins, weights) entry,
+ * nerf_process.py:144; z_c may then be NULL and z_fine must be NULL).  Optional outputs (may be NULL):
+ * z_samples [N,S_f] (unsorted, pre-merge), inds [N,S_f] int64 (torch.searchsorted right=True),
+ * cdf_out [N,S_c-1].  Summation order: row sum and cumsum accumulate in fp64. */
+int nb_sample_pdf(nb_handle_t h, int64_t N, int32_t S_c, int32_t S_f, const float* z_c, const float* weights_c,
+                  const float* u, int32_t u_mode, uint64_t seed, uint64_t offset, const float* cdf_in,
+                  const float* bins_in, float* z_fine, float* z_samples, int64_t* inds, float* cdf_out, void* stream);
+
+/* ---- K3: positional encoding (materialised form) ---------------------------------------- */
+/* model/PositionalEncoding.py:29-30: out[p] = [x, sin(2^k x), cos(2^k x)]_{k<L}; out is [P, 3+6L]. */
+int nb_posenc(nb_handle_t h, int64_t P, int32_t L, const float* x, float* out, void* stream);
+/* nerf_process.py:34-39,69-85: embedded[n*S+s, :] = [PE_Lx(o+d*z), PE_Ld(d/|d|)], row stride ld_out
+ * floats (>= 6+6Lx+6Ld); columns beyond the 90 features are left untouched. */
+int nb_embed_points(nb_handle_t h, int64_t N, int32_t S, int32_t L_x, int32_t L_d, const float* rays,
+                    const float* z, float* out, int64_t ld_out, void* stream);
+
+/* ---- K4: MLP ---------------------------------------------------------------------------- */
+/* Bytes of the activation stash forward() fills for backward() (P points). */
+int nb_mlp_act_bytes(nb_handle_t h, const nb_mlp_desc* d, int64_t P, int32_t precision, size_t* out);
+/* Scratch bytes needed by forward/backward for P points. */
+int nb_mlp_workspace_bytes(nb_handle_t h, const nb_mlp_desc* d, int64_t P, int32_t precision, int32_t backward,
+                           size_t* out);
+/* Bytes of the packed (tile-layout bf16) copy of one net's weights and the packer itself
+ * (call after load_state_dict / every optimizer step).  NB_BF16 only. */
+int nb_mlp_packed_bytes(nb_handle_t h, const nb_mlp_desc* d, size_t* out);
+int nb_mlp_pack(nb_handle_t h, const nb_mlp_desc* d, const float* params, void* packed, void* stream);
+/* model/NeRF.py:33-52 on a materialised embedding x[P, ld_x] (first in_x+in_d columns used):
+ * raw_out[P,4] = [rgb, sigma].  act_save NULL in inference. */
+int nb_mlp_forward_emb(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t P,
+                       const float* x, int64_t ld_x, float* raw_out, void* act_save, int32_t precision,
+                       void* ws, size_t ws_bytes, void* stream);
+/* Fused form used by render_rays (nerf_process.py:187-194 / 202-209): points and both encodings
+ * are generated from rays[N,6], z[N,S]; the [N*S,90] tensor is never materialised in NB_BF16. */
+int nb_mlp_forward_rays(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t N,
+                        int32_t S, const float* rays, const float* z, float* raw_out, void* act_save,
+                        int32_t precision, void* ws, size_t ws_bytes, void* stream);
+/* Autograd of the above wrt the parameters (train.py:69): grad (flat, params layout) = or += dL/dparams
+ * given d_raw[P,4] and the stash written by forward. */
+int nb_mlp_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t P,
+                    const void* act_save, const float* d_raw, float* grad, int32_t accumulate, int32_t precision,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K5: compositing -------------------------------------------------------------------- */
+/* nerf_process.py:89-140 post_process: raw[N,S,4], z[N,S], rays_d[N,3] -> rgb[N,3], disp[N], acc[N],
+ * weights[N,S], depth[N].  Any output except rgb may be NULL. */
+int nb_composite_forward(nb_handle_t h, int64_t N, int32_t S, const float* raw, const float* z, const float* rays_d,
+                         float* rgb, float* disp, float* acc, float* weights, float* depth, void* stream);
+/* Autograd of post_process wrt raw for an upstream gradient on rgb_map (train.py:60-66), fused:
+ * d_raw[N,S,4].  d_rgb is [N,3]. */
+int nb_composite_backward(nb_handle_t h, int64_t N, int32_t S, const float* raw, const float* z, const float* rays_d,
+                          const float* d_rgb, float* d_raw, void* stream);
+
+/* ---- loss / optimizer ----------------------------------------------------- */
+/* train.py:58-65 nn.MSELoss: d_rgb = scale*(rgb-target) with scale = 2/(3*N_global);
+ * loss_out (device scalar, optional) += sum((rgb-target)^2) * loss_scale. */
+int nb_mse_grad(nb_handle_t h, int64_t N, const float* rgb, const float* target, float scale, float loss_scale,
+                float* d_rgb, float* loss_out, void* stream);
+/* main.py:79-80 torch.optim.Adam(betas, eps, no weight decay) on flat buffers; step is 1-based. */
+int nb_adam_step(nb_handle_t h, int64_t n, float* p, const float* g, float* m, float* v, float lr, float beta1,
+                 float beta2, float eps, int32_t step, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_B200_H_ */

@@ -1,0 +1,206 @@
+// K2: stratified coarse sampling and hierarchical inverse-CDF fine sampling.
+//
+// Replaces nerf_process.py:43-60 (coarse z with unconditional jitter) and nerf_process.py:62-67 +
+// 144-182 (mids, pdf, cdf, searchsorted, gather, lerp, cat, sort).  HBM-bound: coarse 536 B/ray,
+// fine 1792 B/ray.  The fine kernel is warp-cooperative: one warp owns one ray, the
+// ray's z / weights / cdf live in shared memory, each lane inverts S_f/32 samples by binary search
+// and the merged S_c+S_f depths are sorted with a shared-memory bitonic network.
+// All contractual fp32 operations are individually rounded (no FMA contraction).
+#include "nb_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// coarse: z[n,s] = lower[s] + span[s] * t_rand[n,s]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stratified_kernel(long long total4, int S, const float* __restrict__ lower, const float* __restrict__ span,
+                  const float4* __restrict__ t_rand, uint2 key, unsigned long long offset,
+                  float4* __restrict__ z_out) {
+  extern __shared__ float s_ls[];  // lower[S], span[S]
+  for (int i = threadIdx.x; i < S; i += blockDim.x) { s_ls[i] = lower[i]; s_ls[S + i] = span[i]; }
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    float4 r;
+    if (t_rand) {
+      r = __ldg(&t_rand[i]);
+    } else {
+      unsigned long long c = offset + (unsigned long long)i;
+      uint4 x = nb_philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), key);
+      r = make_float4(nb_u01(x.x), nb_u01(x.y), nb_u01(x.z), nb_u01(x.w));
+    }
+    int s = (int)((i * 4) % S);   // S % 4 == 0, so the 4 samples stay inside one ray
+    float4 z;
+    z.x = __fadd_rn(s_ls[s + 0], __fmul_rn(s_ls[S + s + 0], r.x));
+    z.y = __fadd_rn(s_ls[s + 1], __fmul_rn(s_ls[S + s + 1], r.y));
+    z.z = __fadd_rn(s_ls[s + 2], __fmul_rn(s_ls[S + s + 2], r.z));
+    z.w = __fadd_rn(s_ls[s + 3], __fmul_rn(s_ls[S + s + 3], r.w));
+    z_out[i] = z;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fine: one warp per ray
+// ------------------------------------------------------------------------------------------
+constexpr int kWarpsPerBlock = 4;
+
+// per-warp smem layout (floats): z[S_c] | cdf[S_c] (S_c-1 knots; holds w during the build) | bins[S_c] | sort[P2]
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sample_pdf_kernel(long long N, int S_c, int S_f, int P2, const float* __restrict__ z_c, const float* __restrict__ w_c,
+                  const float* __restrict__ u_in, int u_mode, uint2 key, unsigned long long offset,
+                  const float* __restrict__ cdf_in, const float* __restrict__ bins_in, float* __restrict__ z_fine,
+                  float* __restrict__ z_samples, long long* __restrict__ inds_out, float* __restrict__ cdf_out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_warp = 3 * S_c + P2;
+  float* sz = smem + warp * per_warp;
+  float* scdf = sz + S_c;          // S_c-1 knots (index 0 is the leading zero)
+  float* sbins = scdf + S_c;       // S_c-1 bin positions
+  float* ssort = sbins + S_c;
+  const int n_knots = S_c - 1;     // len(bins) = len(cdf)
+  const int n_w = S_c - 2;         // weights[..., 1:-1]
+  const int S = S_c + S_f;
+
+  for (long long ray = (long long)blockIdx.x * kWarpsPerBlock + warp; ray < N; ray += (long long)gridDim.x * kWarpsPerBlock) {
+    // ---- stage z and w (coalesced) ----
+    if (z_c) for (int i = lane; i < S_c; i += 32) sz[i] = z_c[ray * S_c + i];
+    __syncwarp();
+    // bins = mids of z (nerf_process.py:63), or given directly (stand-alone sample_pdf entry)
+    for (int i = lane; i < n_knots; i += 32)
+      sbins[i] = bins_in ? bins_in[ray * n_knots + i] : __fmul_rn(0.5f, __fadd_rn(sz[i + 1], sz[i]));
+    if (cdf_in) {
+      for (int i = lane; i < n_knots; i += 32) scdf[i] = cdf_in[ray * n_knots + i];
+      __syncwarp();
+    } else {
+      // w = weights[1:-1] + 1e-5 ; pdf = w / sum(w) ; cdf = [0, cumsum(pdf)]   (nerf_process.py:150-155)
+      // sum and cumsum accumulate in fp64 (order-independent to fp32 precision; DESIGN.md "summation order")
+      double part = 0.0;
+      for (int i = lane; i < n_w; i += 32) {
+        float w = __fadd_rn(w_c[ray * S_c + 1 + i], 1e-5f);
+        scdf[1 + i] = w;
+        part += (double)w;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      const float total = (float)part;
+      __syncwarp();
+      // inclusive scan over n_w (<=  a few hundred) values: chunks of 32 with a running carry
+      double carry = 0.0;
+      for (int base = 0; base < n_w; base += 32) {
+        int i = base + lane;
+        double v = (i < n_w) ? (double)__fdiv_rn(scdf[1 + i], total) : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          double t = __shfl_up_sync(0xffffffffu, v, o);
+          if (lane >= o) v += t;
+        }
+        v += carry;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+        __syncwarp();
+        if (i < n_w) scdf[1 + i] = (float)v;
+      }
+      if (lane == 0) scdf[0] = 0.0f;
+      __syncwarp();
+    }
+    if (cdf_out) for (int i = lane; i < n_knots; i += 32) cdf_out[ray * n_knots + i] = scdf[i];
+
+    // ---- invert the cdf for S_f samples ----
+    for (int j = lane; j < S_f; j += 32) {
+      float u;
+      if (u_mode == 0) u = u_in[j];
+      else if (u_mode == 1) u = u_in[ray * S_f + j];
+      else {
+        const unsigned long long e = (unsigned long long)(ray * S_f + j);
+        const unsigned long long c = offset + (e >> 2);
+        uint4 x = nb_philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 1u, 0u), key);
+        const int q = (int)(e & 3);
+        u = nb_u01(q == 0 ? x.x : q == 1 ? x.y : q == 2 ? x.z : x.w);
+      }
+      // searchsorted(cdf, u, right=True): first index with cdf[idx] > u, in [0, n_knots]
+      int lo = 0, hi = n_knots;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (scdf[mid] <= u) lo = mid + 1; else hi = mid;
+      }
+      const int ind = lo;
+      const int below = max(0, ind - 1), above = min(n_knots - 1, ind);
+      const float cb = scdf[below], ca = scdf[above];
+      const float bb = sbins[below], ba = sbins[above];
+      float denom = __fsub_rn(ca, cb);
+      if (denom < 1e-5f) denom = 1.0f;
+      const float t = __fdiv_rn(__fsub_rn(u, cb), denom);
+      const float zs = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+      if (z_fine) ssort[S_c + j] = zs;
+      if (z_samples) z_samples[ray * S_f + j] = zs;
+      if (inds_out) inds_out[ray * S_f + j] = ind;
+    }
+    if (!z_fine) { __syncwarp(); continue; }   // warp-uniform: samples only
+    for (int i = lane; i < S_c; i += 32) ssort[i] = sz[i];
+    for (int i = S + lane; i < P2; i += 32) ssort[i] = __int_as_float(0x7f800000);  // +inf padding
+    __syncwarp();
+
+    // ---- bitonic sort of P2 values (torch.sort(cat([z, z_samples])), values only) ----
+    for (int k = 2; k <= P2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < (P2 >> 1); t += 32) {
+          int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j cleared
+          int p = i | j;
+          bool up = ((i & k) == 0);
+          float a = ssort[i], b = ssort[p];
+          if ((a > b) == up) { ssort[i] = b; ssort[p] = a; }
+        }
+        __syncwarp();
+      }
+    }
+    for (int i = lane; i < S; i += 32) z_fine[ray * S + i] = ssort[i];
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+extern "C" int nb_stratified(nb_handle_t h, int64_t N, int32_t S_c, const float* lower, const float* span,
+                             const float* t_rand, uint64_t seed, uint64_t offset, float* z_out, void* stream) {
+  NB_ENTER(h);
+  NB_REQUIRE(h, N >= 0 && S_c > 0 && S_c % 4 == 0 && S_c <= 2048 && lower && span && z_out,
+             "nb_stratified: need S_c %% 4 == 0, S_c <= 2048 and non-null buffers");
+  if (N == 0) return NB_OK;
+  const long long total4 = (long long)N * S_c / 4;
+  int blocks = (int)((total4 + 255) / 256);
+  const int cap = h->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  stratified_kernel<<<blocks, 256, 2 * S_c * sizeof(float), (cudaStream_t)stream>>>(
+      total4, S_c, lower, span, (const float4*)t_rand, key, (unsigned long long)offset, (float4*)z_out);
+  NB_LAUNCHED(h);
+  return NB_OK;
+}
+
+extern "C" int nb_sample_pdf(nb_handle_t h, int64_t N, int32_t S_c, int32_t S_f, const float* z_c,
+                             const float* weights_c, const float* u, int32_t u_mode, uint64_t seed, uint64_t offset,
+                             const float* cdf_in, const float* bins_in, float* z_fine, float* z_samples, int64_t* inds,
+                             float* cdf_out, void* stream) {
+  NB_ENTER(h);
+  NB_REQUIRE(h, N >= 0 && S_c >= 3 && S_f > 0 && S_c + S_f <= 4096, "nb_sample_pdf: bad sizes");
+  NB_REQUIRE(h, z_c || (bins_in && !z_fine), "nb_sample_pdf: z_c may be NULL only with bins_in and without z_fine");
+  NB_REQUIRE(h, z_fine || z_samples || inds || cdf_out, "nb_sample_pdf: no output requested");
+  NB_REQUIRE(h, weights_c || cdf_in, "nb_sample_pdf: need weights or cdf_in");
+  NB_REQUIRE(h, u_mode >= 0 && u_mode <= 2 && (u_mode == 2 || u), "nb_sample_pdf: bad u / u_mode");
+  if (N == 0) return NB_OK;
+  int P2 = 1;
+  while (P2 < S_c + S_f) P2 <<= 1;
+  const size_t smem = (size_t)kWarpsPerBlock * (3 * S_c + P2) * sizeof(float);
+  NB_REQUIRE(h, smem <= 200 * 1024, "nb_sample_pdf: S_c/S_f too large for shared memory");
+  if (smem > 48 * 1024)
+    NB_CUDA(h, cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long blocks = (N + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const long long cap = (long long)h->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  sample_pdf_kernel<<<(int)blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+      (long long)N, S_c, S_f, P2, z_c, weights_c, u, u_mode, key, (unsigned long long)offset, cdf_in, bins_in, z_fine,
+      z_samples, (long long*)inds, cdf_out);
+  NB_LAUNCHED(h);
+  return NB_OK;
+}
