@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the ray-batch hot path (BASELINE.json: train rays/s at 4096 rays, 64+128 samples).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+
+One "step" = one full train step (ray batch -> coarse+fine render -> MSE_c+MSE_f -> backward ->
+Adam) on 4096 rays PER GPU (weak scaling) of the Blender-lego-shaped synthetic workload
+(BASELINE.json configs[1]).  Prints ONE JSON line (rank 0).  `value` times the step with the ray
+batch already resident in HBM; `e2e` times the reference-facing call train.train(...) with the
+target image and pixel indices coming from pinned HOST memory every step and the loss read back.
+`--impl reference` times the CPU restatement of the reference (oracle/, numpy+BLAS on all host
+cores) on a bounded sample of the same workload; under torchrun only rank 0 runs it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RAYS, S_C, S_F = 4096, 64, 128
+H = W = 800
+FOCAL = 0.5 * 800 / np.tan(0.5 * 0.6911112070083618)        # load_blender.py:51-52 -> 1111.111
+FLOP_PER_POINT_TRAIN = 3489024                              # fwd 1,186,816 + bwd 2,302,208
+FLOP_PER_POINT_FWD = 1186816
+POINTS_PER_RAY = S_C + (S_C + S_F)                          # coarse net sees 64, fine net all 192
+WORKLOAD = 'Blender lego-shaped train step: 4096 rays/batch per GPU, 64+128 samples, PE L=10/4, 8x256 skip MLP x2, Adam'
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('bf16_tflops_sustained', 1373.4), d.get('hbm_gbs', 6549.8), 'measured (MEASURED_PEAKS.json, sustained bf16)'
+    return 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def synthetic_poses(n, seed=0):
+    """Blender-shaped c2w poses on a radius-4 sphere (the generator of dataset/render_pose.py:28-34,
+    theta~U(-180,180), phi~U(-90,0)), restated with numpy."""
+    rs = np.random.RandomState(seed)
+    out = []
+    for _ in range(n):
+        th, phi = np.deg2rad(rs.uniform(-180, 180)), np.deg2rad(rs.uniform(-90, 0))
+        t = np.eye(4); t[2, 3] = 4.0
+        rp = np.array([[1, 0, 0, 0], [0, np.cos(phi), -np.sin(phi), 0], [0, np.sin(phi), np.cos(phi), 0], [0, 0, 0, 1]])
+        rt = np.array([[np.cos(th), 0, -np.sin(th), 0], [0, 1, 0, 0], [np.sin(th), 0, np.cos(th), 0], [0, 0, 0, 1]])
+        c2w = np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]]) @ rt @ rp @ t
+        out.append(c2w)
+    return np.stack(out).astype(np.float32)
+
+
+def make_opts(rank_dev=0, **kw):
+    base = dict(near=2., far=6., N_samples_c=S_C, N_samples_f=S_F, perturb=1., data_type='blender', gpu_ids=[rank_dev], rank=0,
+                chunk_rays=N_RAYS, chunk_pts=524288, N_rays=N_RAYS, precrop_iters=0, precrop_frac=.5, seed=0,
+                global_batch=False, idx_print=10 ** 9, idx_save=None, exp_name='bench')
+    base.update(kw)
+    return SimpleNamespace(**base)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the numpy oracle on all host cores, bounded sample
+# ----------------------------------------------------------------------------------------------
+def cpu_port_step(n_rays, seed=0):
+    """One train step (render + grads + Adam) of the oracle port on n_rays rays; returns seconds."""
+    from oracle import nerf_oracle as orc
+    rs = np.random.RandomState(seed)
+    if not hasattr(cpu_port_step, 'state'):
+        import torch
+        torch.manual_seed(0)
+        from nerf_pytorch_paeng_b200.model import NeRF           # host-side module: only for the reference's seeded init
+        net = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None))
+        sd = {k: v.detach().numpy().copy() for k, v in net.state_dict().items()}
+        pc = {k[len('model_coarse.'):]: v for k, v in sd.items() if k.startswith('model_coarse.')}
+        pf = {k[len('model_fine.'):]: v for k, v in sd.items() if k.startswith('model_fine.')}
+        pose = synthetic_poses(1)[0]
+        K = np.array([[FOCAL, 0, 400.], [0, FOCAL, 400.], [0, 0, 1.]])
+        o, d = orc.make_o_d(W, H, K, pose[:3, :4])
+        cpu_port_step.state = (pc, pf, o.reshape(-1, 3), d.reshape(-1, 3))
+    pc, pf, o, d = cpu_port_step.state
+    sel = rs.choice(H * W, n_rays, replace=False)
+    rays = np.concatenate([o[sel], d[sel]], -1)
+    target = rs.rand(n_rays, 3).astype(np.float32)
+    t_rand, u = rs.rand(n_rays, S_C).astype(np.float32), rs.rand(n_rays, S_F).astype(np.float32)
+    t0 = time.perf_counter()
+    lc, lf, gc, gf = orc.train_grads(rays, target, pc, pf, orc.make_opts(), t_rand, u)
+    for p, g in ((pc, gc), (pf, gf)):
+        for k in p:
+            p[k], _, _ = orc.adam_step(p[k], g[k], np.zeros_like(g[k]), np.zeros_like(g[k]), 1, 5e-4)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n = args.cpu_rays
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_port_step(n)
+    times = [cpu_port_step(n, seed=i + 1) for i in range(max(1, min(args.steps, 5)))]
+    ms = 1e3 * float(np.mean(times))
+    val = n / (ms / 1e3)
+    cores = os.cpu_count()
+    line = {'impl': 'reference', 'metric': 'train_rays_per_s', 'value': val, 'unit': 'rays/s', 'n_gpus': args.gpus,
+            'steps': len(times), 'warmup': max(1, min(args.warmup, 2)), 'ms_per_step': ms, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'sample': f'{n} rays per step (bounded sample of the 4096-ray batch)'},
+            'cpu_baseline': {'value': val, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{n}-ray train step (render+grads+Adam) of oracle/nerf_oracle.py, numpy/BLAS threads={cores}'},
+            'e2e': {'value': val, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from nerf_pytorch_paeng_b200 import distributed, train as train_mod, trainer
+    from nerf_pytorch_paeng_b200.engine import get_engine
+    from nerf_pytorch_paeng_b200.model import NeRF, get_positional_encoder
+
+    dctx = distributed.init_from_env('nccl')
+    rank = dctx.rank if dctx else 0
+    world = dctx.world_size if dctx else 1
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    eng = get_engine(dev)
+    torch.manual_seed(0)
+    model = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).to(dev)      # random init, identical on every rank
+    model.set_precision(args.precision)
+    opts = make_opts(rank_dev=local, seed=1000 + rank)
+    optimizer = trainer.FlatAdam(model, lr=5e-4)
+    posenc = [get_positional_encoder(10)[0], get_positional_encoder(4)[0]]
+    K = np.array([[FOCAL, 0, 400.], [0, FOCAL, 400.], [0, 0, 1.]])
+    poses = synthetic_poses(16, seed=0)
+    poses_dev = torch.from_numpy(poses).to(dev)
+
+    # ---- resident inputs: a ring of pre-generated ray batches (different pose/pixels per step, per rank)
+    n_ring = 8
+    gen = torch.Generator(device='cpu').manual_seed(1234 + rank)
+    ring = []
+    for i in range(n_ring):
+        pix = torch.randperm(H * W, generator=gen)[:N_RAYS].to(dev)
+        o, d = eng.raygen(H, W, K, poses_dev[i % len(poses), :3, :4], pix_idx=pix)
+        ring.append((torch.cat((o, d), -1), torch.rand(N_RAYS, 3, device=dev)))
+
+    def barrier():
+        if dctx:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        rays, tgt = ring[i % n_ring]
+        return trainer.train_step(model, optimizer, rays, tgt, opts, dist_ctx=dctx)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        loss = step(i)
+    ev1.record()
+    barrier()
+    launches = eng.launch_count() - l0
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], device=dev)
+    if dctx:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_step = float(t) / args.steps
+    value = N_RAYS * world / (ms_step / 1e3)
+
+    # ---- roofline of the dominant kernels (the MLP): CUDA events around every MLP call of K steps
+    mlp_ms, mlp_calls = [0.0], [0]
+    of, ob = eng.mlp_forward, eng.mlp_backward
+    pend = []
+
+    def timed(fn):
+        def wrap(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            pend.append((e0, e1))
+            mlp_calls[0] += 1
+            return r
+        return wrap
+    eng.mlp_forward, eng.mlp_backward = timed(of), timed(ob)
+    lm0 = eng.launch_count()
+    n_prof = min(args.steps, 5)
+    for i in range(n_prof):
+        step(i)
+    torch.cuda.synchronize()
+    eng.mlp_forward, eng.mlp_backward = of, ob
+    mlp_ms = sum(a.elapsed_time(b) for a, b in pend) / n_prof
+    flop_step = FLOP_PER_POINT_TRAIN * N_RAYS * POINTS_PER_RAY
+    peak_tf, peak_hbm, peak_src = peaks()
+    achieved = flop_step / (mlp_ms / 1e3) / 1e12
+    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+                'traffic': None, 'kernel': 'MLP forward+backward (4 calls/step: coarse+fine fwd, coarse+fine bwd)',
+                'algorithmic_flop_per_step': flop_step, 'mlp_ms_per_step': mlp_ms, 'mlp_share_of_step': mlp_ms / ms_step,
+                'peak_source': peak_src}
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: the reference-facing call train.train(...) with HOST inputs every step
+    n_img = 4
+    images = [torch.rand(H, W, 3).pin_memory() for _ in range(n_img)]
+    gt_cam = (K, poses[:n_img])
+    crit = torch.nn.MSELoss()
+    np.random.seed(rank)
+    host_loss = torch.zeros(1).pin_memory()
+
+    def e2e_step(i):
+        loss = train_mod.train(i + 1, list(range(n_img)), images, gt_cam, (H, W), model, crit, posenc, optimizer, None, None, opts,
+                               dist_ctx=dctx)
+        host_loss.copy_(loss.reshape(1), non_blocking=False)      # D2H read of the step's result
+        return float(host_loss)
+    for i in range(max(3, args.warmup // 2)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], device=dev)
+    if dctx:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    e2e_ms_step = float(t) / args.steps
+    e2e = {'value': N_RAYS * world / (e2e_ms_step / 1e3), 'unit': 'rays/s', 'ms_per_step': e2e_ms_step,
+           'h2d_bytes_per_step': H * W * 3 * 4 + N_RAYS * 8, 'd2h_bytes_per_step': 4,
+           'api': 'nerf_pytorch_paeng_b200.train.train (per-image path, train.py:35-45: pinned host image -> H2D, '
+                  'np.random.choice pixel selection on host, ray-gen + gather + fused step on device, loss D2H)'}
+
+    if rank != 0:
+        return
+    # ---- cpu baseline on this box's host cores (bounded sample)
+    cpu = None
+    if not args.no_cpu:
+        cpu_port_step(args.cpu_rays)
+        ts = [cpu_port_step(args.cpu_rays, seed=i + 1) for i in range(2)]
+        cpu = {'value': args.cpu_rays / float(np.mean(ts)), 'unit': 'rays/s', 'cores': os.cpu_count(), 'kind': 'port',
+               'sample': f'{args.cpu_rays}-ray train step (render+grads+Adam) of oracle/nerf_oracle.py, numpy/BLAS on all host cores'}
+    line = {'metric': 'train_rays_per_s', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'rays_per_gpu': N_RAYS, 'global_rays': N_RAYS * world, 'samples': [S_C, S_F],
+                       'precision': args.precision, 'parallelism': f'ray-sharded data parallel x{world}, NCCL all-reduce of 2x595,844 fp32 grads',
+                       'l2': 'per-step working set (activation stash >= 5 GB) exceeds the 126 MB L2; ring of 8 distinct ray batches',
+                       'loss': float(loss.sum())},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
+            'gpu_launches_per_step': launches / args.steps}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', type=str, default=os.environ.get('NB_PRECISION', 'fp32'), choices=['fp32', 'bf16'])
+    ap.add_argument('--cpu-rays', dest='cpu_rays', type=int, default=256)
+    ap.add_argument('--no-cpu', dest='no_cpu', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

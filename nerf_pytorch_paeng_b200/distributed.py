@@ -1,0 +1,65 @@
+"""Multi-GPU plumbing: one process per GPU, rays sharded across ranks.
+
+Render needs only a final gather of the per-rank pixel bands; training is data parallel with one
+all-reduce (sum) of each network's flat fp32 gradient buffer (595,844 floats per net) -- NCCL over
+NVLink/NVSwitch on GPUs, gloo in the CPU tests of this host-side logic.  The reference has no
+distributed code at all (main.py:166-171 is a FIXME), so there is no reference collective to mirror.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world_size):
+    """Contiguous, balanced [lo, hi) band of n items for `rank` (first n % world ranks get one extra)."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class DistContext:
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world_size = dist.get_world_size(group)
+
+    def shard_range(self, n):
+        return shard_range(n, self.rank, self.world_size)
+
+    def allreduce_(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def allreduce_grads(self, model):
+        """Sum the two flat gradient buffers over ranks.  The loss of every rank is normalised by the
+        GLOBAL ray count, so the sum equals the single-GPU gradient of the concatenated batch."""
+        works = []
+        for net in (model.model_coarse, model.model_fine):
+            g = net.bind_flat_grad()
+            works.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for w in works:
+            w.wait()
+
+    def gather_rows(self, local, n_total):
+        """All-gather variable-length row bands (dim 0) into the full [n_total, ...] tensor."""
+        sizes = [shard_range(n_total, r, self.world_size) for r in range(self.world_size)]
+        maxlen = max(hi - lo for lo, hi in sizes)
+        pad = torch.zeros((maxlen,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+        bufs = [torch.empty_like(pad) for _ in range(self.world_size)]
+        dist.all_gather(bufs, pad, group=self.group)
+        return torch.cat([b[:hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
+
+
+def init_from_env(backend=None):
+    """torchrun-style init (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT)."""
+    import os
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world <= 1:
+        return None
+    if not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+        dist.init_process_group(backend=backend)
+    return DistContext()

@@ -1,0 +1,108 @@
+"""Drop-in for the reference's train.py:12-119 (file:line refs into the reference).
+
+Same signature.  What changes underneath: the selected rays are generated directly by the ray-gen
+kernel (only N_rays of the H*W pixels), render + loss + backward run as the fused
+no-autograd step of trainer.py when `criterion` is an MSELoss, and gradients are exposed to the
+caller's optimizer through p.grad views of the flat gradient buffers (so torch.optim.Adam keeps
+working) -- or updated by trainer.FlatAdam in one launch per network.  Visdom plotting and the
+matplotlib camera plot (train.py:73-102,117-119) are out of scope; the print line and the
+checkpoint dict/cadence (train.py:105-114) are kept.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import trainer
+from .config import LOG_DIR
+from .nerf_process import batchify_rays_and_render_by_chunk, ndc_rays
+from .rays import make_o_d_selected
+from .utils import mse2psnr
+
+_cache = {}
+
+
+def _device_copy(arr, device, key):
+    """K / poses: the reference re-uploads them every step (train.py:18-21); here once per array."""
+    k = (key, id(arr), str(device))
+    if k not in _cache:
+        _cache[k] = torch.from_numpy(np.ascontiguousarray(arr)).to(device)
+    return _cache[k]
+
+
+def select_pixels(i, img_h, img_w, opts):
+    """rays.py:40-54: indices of N_rays distinct pixels (centre crop while i < precrop_iters); same
+    host RNG call as the reference so seeded runs pick the same pixels."""
+    if i < opts.precrop_iters:
+        dH = int(img_h // 2 * opts.precrop_frac)
+        dW = int(img_w // 2 * opts.precrop_frac)
+        rows = np.arange(img_h // 2 - dH, img_h // 2 + dH)
+        cols = np.arange(img_w // 2 - dW, img_w // 2 + dW)
+    else:
+        rows, cols = np.arange(img_h), np.arange(img_w)
+    sel = np.random.choice(a=rows.size * cols.size, size=opts.N_rays, replace=False)
+    return (rows[sel // cols.size] * img_w + cols[sel % cols.size]).astype(np.int64)
+
+
+def train(idx, i_train, images, gt_cam_param, hw, model, criterion, posenc, optimizer, global_batch_idx, vis, opts,
+          dist_ctx=None):
+    model.train()
+    device = torch.device(f'cuda:{opts.gpu_ids[opts.rank]}')
+    img_h, img_w = hw
+    gt_intrinsic, gt_extrinsic = gt_cam_param
+    llff = opts.data_type == 'llff'
+
+    if global_batch_idx is not None and opts.global_batch:                       # train.py:25-32
+        i_batch, rays_rgb, epoch = global_batch_idx(opts.N_rays)
+        batch = rays_rgb[i_batch - opts.N_rays:i_batch]
+        rays_o, rays_d, target = batch[:, 0].contiguous(), batch[:, 1].contiguous(), batch[:, 2].contiguous()
+        if llff:
+            rays_o, rays_d = ndc_rays(img_h, img_w, float(gt_intrinsic[0][0]), 1., rays_o, rays_d)
+    else:                                                                         # train.py:35-45
+        i_img = np.random.choice(i_train)
+        pose = _device_copy(gt_extrinsic, device, 'poses')[i_img, :3, :4]
+        pix = torch.from_numpy(select_pixels(idx, img_h, img_w, opts)).to(device, non_blocking=True)
+        img = images[i_img]
+        img = img if isinstance(img, torch.Tensor) else torch.from_numpy(img)
+        img = img.to(device=device, dtype=torch.float32, non_blocking=True)      # H2D of the target image
+        rays_o, rays_d = make_o_d_selected(img_w, img_h, gt_intrinsic, pose, pix, ndc=llff, near=1.)
+        from .engine import get_engine
+        target = get_engine(device).gather_rows(img.reshape(-1, 3), pix)
+    rays = torch.cat((rays_o, rays_d), dim=-1)
+
+    fused = isinstance(criterion, torch.nn.MSELoss) or criterion is None
+    if fused:
+        for net in (model.model_coarse, model.model_fine):
+            net.bind_flat_grad()
+        if not isinstance(optimizer, trainer.FlatAdam):
+            optimizer.zero_grad(set_to_none=False)
+        loss_buf = trainer.train_step(model, optimizer, rays, target, opts, dist_ctx=dist_ctx)
+        loss_c, loss_f = loss_buf[0], loss_buf[1]
+        loss = loss_c + loss_f
+    else:                                                                         # generic criterion: autograd path
+        saved = opts.data_type
+        opts.data_type = 'blender'                                               # rays are already warped
+        try:
+            rgb_c, _, rgb_f, _ = batchify_rays_and_render_by_chunk(rays_o, rays_d, model, posenc, img_h, img_w, gt_intrinsic, opts)
+        finally:
+            opts.data_type = saved
+        optimizer.zero_grad()
+        loss_c = criterion(rgb_c, target)
+        loss_f = criterion(rgb_f, target) if opts.N_samples_f > 0 else torch.zeros_like(loss_c)
+        loss = loss_c + loss_f
+        loss.backward()
+        optimizer.step()
+
+    if idx % opts.idx_print == 0:                                                # the only sync point (train.py:73-77)
+        if opts.N_samples_f > 0:
+            print('i : {} , Loss_C : {} , Loss_F : {} , Total_Loss : {} , PSNR_C : {} , PSNR_F : {}'.format(
+                idx, float(loss_c), float(loss_f), float(loss), float(mse2psnr(loss_c.reshape(1))), float(mse2psnr(loss_f.reshape(1)))))
+        else:
+            print('i : {} , LOSS : {} , PSNR : {}'.format(idx, float(loss), float(mse2psnr(loss.reshape(1)))))
+
+    if opts.idx_save and idx % opts.idx_save == 0 and idx > 0 and (dist_ctx is None or dist_ctx.rank == 0):   # train.py:105-114
+        save_path = os.path.join(LOG_DIR, opts.exp_name)
+        os.makedirs(save_path, exist_ok=True)
+        checkpoint = {'idx': idx, 'model_state_dict': model.state_dict(), 'optimizer_state_dict': optimizer.state_dict()}
+        torch.save(checkpoint, os.path.join(save_path, opts.exp_name + '_{}.pth.tar'.format(idx)))
+    return loss

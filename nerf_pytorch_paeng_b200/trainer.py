@@ -1,0 +1,153 @@
+"""Fused train step / frame render drivers (the path bench.py measures).
+
+``train_step`` is train.py:53-70 of the reference (render coarse+fine, MSE_c + MSE_f, backward,
+Adam) without autograd: every stage is one call into libnerf_b200.so, gradients land in one flat
+fp32 buffer per network (so data-parallel training is a single NCCL all-reduce over it), and Adam
+runs over the flat parameter buffer.  ``render_frame`` is test.py:38-40 (make_o_d -> batchify).
+"""
+import torch
+
+from . import nerf_process as NP
+from .engine import get_engine
+
+
+class FlatAdam:
+    """torch.optim.Adam(lr, betas=(0.9,0.999), eps=1e-8) (main.py:79-80) over the model's two flat
+    parameter buffers, one nb_adam_step launch per network."""
+
+    def __init__(self, model, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
+        self.model = model
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.step_count = 0
+        self.state = {}
+        self.param_groups = [{'lr': lr}]          # so reference-style LR schedulers can poke ['lr']
+
+    def _nets(self):
+        return (self.model.model_coarse, self.model.model_fine)
+
+    def zero_grad(self, set_to_none=False):
+        for net in self._nets():
+            if net.flat_grad is not None:
+                net.flat_grad.zero_()
+
+    def step(self):
+        self.step_count += 1
+        lr = self.param_groups[0]['lr']
+        for net in self._nets():
+            flat = net.flat_params()
+            grad = net.bind_flat_grad()
+            eng = get_engine(flat.device)
+            st = self.state.get(id(net))
+            if st is None or st[0].shape != flat.shape or st[0].device != flat.device:
+                st = (torch.zeros_like(flat), torch.zeros_like(flat))
+                self.state[id(net)] = st
+            eng.adam_step(flat, grad, st[0], st[1], lr, self.step_count, self.betas[0], self.betas[1], self.eps)
+            net.mark_weights_changed()
+
+    def state_dict(self):
+        return {'step': self.step_count, 'lr': self.param_groups[0]['lr'],
+                'state': [tuple(t.clone() for t in self.state[id(n)]) if id(n) in self.state else None for n in self._nets()]}
+
+    def load_state_dict(self, sd):
+        self.step_count = sd['step']
+        self.param_groups[0]['lr'] = sd['lr']
+        for n, st in zip(self._nets(), sd['state']):
+            if st is not None:
+                self.state[id(n)] = tuple(t.clone() for t in st)
+
+
+def render_losses_and_grads(model, rays, target, opts, n_global=None, want_grads=True, loss_buf=None):
+    """Forward coarse+fine, loss, and (optionally) parameter gradients into the flat buffers.
+
+    rays [N,6] (already NDC-warped for llff), target [N,3].  n_global: total rays over all ranks
+    (the MSE mean is over the GLOBAL batch so that summed rank gradients equal the single-GPU
+    gradient).  Returns dict(rgb_c, rgb_f, disp_c, disp_f, loss_buf[2] device tensor).
+    """
+    eng = get_engine(rays.device)
+    n = rays.shape[0]
+    n_global = n if n_global is None else n_global
+    rays = rays.contiguous()
+    rays_d = rays[:, 3:].contiguous()
+    scale = 2.0 / (3.0 * n_global)
+    if loss_buf is None:
+        loss_buf = torch.zeros(2, device=rays.device)
+    out = {'loss_buf': loss_buf}
+    z_prev = w_prev = None
+    for i, fine in enumerate((False, True)):
+        if fine and opts.N_samples_f <= 0:
+            break
+        net = model.model_fine if fine else model.model_coarse
+        flat = net.flat_params()
+        z = NP._fine_z(rays, opts, z_prev, w_prev) if fine else NP._coarse_z(rays, opts)
+        raw, act = eng.mlp_forward(net.desc, flat, net.packed_weights(), net.precision, rays=rays, z=z, save=want_grads)
+        raw3 = raw.view(n, z.shape[1], 4)
+        rgb, disp, acc, w, depth = eng.composite_forward(raw3, z, rays_d, want_all=not fine)
+        tag = 'f' if fine else 'c'
+        out['rgb_' + tag], out['disp_' + tag] = rgb, disp
+        d_rgb = eng.mse_grad(rgb, target, scale, 1.0 / (3.0 * n_global), loss_buf[i:i + 1], want_grad=want_grads)
+        if want_grads:
+            d_raw = eng.composite_backward(raw3, z, rays_d, d_rgb)
+            grad = net.bind_flat_grad()
+            eng.mlp_backward(net.desc, flat, net.packed_weights(), net.precision, n * z.shape[1], act, d_raw.view(-1, 4), grad)
+            del act
+        z_prev, w_prev = z, w
+    return out
+
+
+def train_step(model, optimizer, rays, target, opts, dist_ctx=None):
+    """One optimisation step on a ray batch; returns the device tensor [loss_c, loss_f] (global means)."""
+    n_global = rays.shape[0] * (dist_ctx.world_size if dist_ctx is not None else 1)
+    out = render_losses_and_grads(model, rays, target, opts, n_global=n_global)
+    if dist_ctx is not None:
+        dist_ctx.allreduce_grads(model)
+        dist_ctx.allreduce_(out['loss_buf'])
+    optimizer.step()
+    return out['loss_buf']
+
+
+@torch.no_grad()
+def render_frame(model, H, W, K, pose, opts, dist_ctx=None, chunk=None):
+    """test.py:38-40: all H*W rays of one pose, coarse+fine.  Rays are generated on the device
+    (ray-gen [+NDC] kernel), rendered in chunks of opts.chunk_rays; with a dist_ctx each rank renders
+    a contiguous band of pixels and the bands are all-gathered.  Returns rgb [H*W,3], disp [H*W]."""
+    eng = get_engine(pose.device)
+    n = H * W
+    lo, hi = (0, n) if dist_ctx is None else dist_ctx.shard_range(n)
+    chunk = chunk or opts.chunk_rays
+    rgb = eng.empty(hi - lo, 3)
+    disp = eng.empty(hi - lo)
+    ndc = opts.data_type == 'llff'
+    use_fine = opts.N_samples_f > 0
+    for s in range(lo, hi, chunk):
+        e = min(hi, s + chunk)
+        pix = torch.arange(s, e, device=pose.device, dtype=torch.int64)
+        o, d = eng.raygen(H, W, K, pose, pix_idx=pix, ndc=ndc, ndc_focal=float(K[0][0]), ndc_near=1.)
+        rays = torch.cat((o, d), dim=-1)
+        out = render_losses_and_grads_free(model, rays, opts)
+        rgb[s - lo:e - lo] = out['rgb_f' if use_fine else 'rgb_c']
+        disp[s - lo:e - lo] = out['disp_f' if use_fine else 'disp_c']
+    if dist_ctx is not None:
+        rgb, disp = dist_ctx.gather_rows(rgb, n), dist_ctx.gather_rows(disp, n)
+    return rgb, disp
+
+
+def render_losses_and_grads_free(model, rays, opts):
+    """Inference-only coarse+fine render of a ray chunk (no loss, no stash)."""
+    eng = get_engine(rays.device)
+    n = rays.shape[0]
+    rays = rays.contiguous()
+    rays_d = rays[:, 3:].contiguous()
+    out = {}
+    z_prev = w_prev = None
+    for fine in (False, True):
+        if fine and opts.N_samples_f <= 0:
+            break
+        net = model.model_fine if fine else model.model_coarse
+        flat = net.flat_params()
+        z = NP._fine_z(rays, opts, z_prev, w_prev) if fine else NP._coarse_z(rays, opts)
+        raw, _ = eng.mlp_forward(net.desc, flat, net.packed_weights(), net.precision, rays=rays, z=z, save=False)
+        rgb, disp, acc, w, depth = eng.composite_forward(raw.view(n, z.shape[1], 4), z, rays_d, want_all=not fine)
+        tag = 'f' if fine else 'c'
+        out['rgb_' + tag], out['disp_' + tag] = rgb, disp
+        z_prev, w_prev = z, w
+    return out

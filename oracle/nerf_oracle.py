@@ -280,11 +280,13 @@ def mlp_forward(params, x, D=8, skips=(4,), input_ch=63, return_acts=False):
     return out
 
 
-def mlp_backward(params, x, d_out, D=8, skips=(4,), input_ch=63):
+def mlp_backward(params, x, d_out, D=8, skips=(4,), input_ch=63, acts=None):
     """Autograd of mlp_forward wrt the parameters (what loss.backward() gives,
     train.py:69).  d_out[n,4] -> dict name -> grad.  Input grads are not needed
-    (sample positions are data, nerf_process.py:66)."""
-    out, acts = mlp_forward(params, x, D, skips, input_ch, return_acts=True)
+    (sample positions are data, nerf_process.py:66).  acts: the forward's saved
+    activations (autograd keeps them; recomputed here only if not supplied)."""
+    if acts is None:
+        _, acts = mlp_forward(params, x, D, skips, input_ch, return_acts=True)
     d_out = _f32(d_out)
     grads = {}
     d_rgb, d_sigma = d_out[:, :3], d_out[:, 3:4]
@@ -393,19 +395,21 @@ def render_rays(rays, params_coarse, params_fine, opts, t_rand, u, D=8, skips=(4
     rays = _f32(rays)
     z_c = stratified_z(opts.near, opts.far, opts.N_samples_c, t_rand)
     emb = embed_points(rays, z_c, L_x, L_d)
-    raw_c = mlp_forward(params_coarse, emb, D, skips, 3 + 6 * L_x).reshape(z_c.shape[0], z_c.shape[1], 4)
+    raw_c, acts_c = mlp_forward(params_coarse, emb, D, skips, 3 + 6 * L_x, return_acts=True)
+    raw_c = raw_c.reshape(z_c.shape[0], z_c.shape[1], 4)
     rgb_c, disp_c, acc_c, w_c, depth_c = post_process(raw_c, z_c, rays[:, 3:])
     ret = {'rgb_c': rgb_c, 'disp_c': disp_c}
     if return_all:
-        ret.update(z_c=z_c, raw_c=raw_c, weights_c=w_c)
+        ret.update(z_c=z_c, raw_c=raw_c, weights_c=w_c, emb_c=emb, acts_c=acts_c)
     if opts.N_samples_f > 0:
         z_f, _, _ = fine_z(z_c, w_c, u)
         emb_f = embed_points(rays, z_f, L_x, L_d)
-        raw_f = mlp_forward(params_fine, emb_f, D, skips, 3 + 6 * L_x).reshape(z_f.shape[0], z_f.shape[1], 4)
+        raw_f, acts_f = mlp_forward(params_fine, emb_f, D, skips, 3 + 6 * L_x, return_acts=True)
+        raw_f = raw_f.reshape(z_f.shape[0], z_f.shape[1], 4)
         rgb_f, disp_f, acc_f, w_f, depth_f = post_process(raw_f, z_f, rays[:, 3:])
         ret.update(rgb_f=rgb_f, disp_f=disp_f)
         if return_all:
-            ret.update(z_f=z_f, raw_f=raw_f, weights_f=w_f)
+            ret.update(z_f=z_f, raw_f=raw_f, weights_f=w_f, emb_f=emb_f, acts_f=acts_f)
     return ret
 
 
@@ -433,8 +437,7 @@ def train_grads(rays, target, params_coarse, params_fine, opts, t_rand, u, D=8, 
         d_rgb = (F32(2.) * diff / n3).astype(np.float32)
         z = r[f'z_{tag}']
         draw = post_process_backward(r[f'raw_{tag}'], z, rays[:, 3:], d_rgb)
-        emb = embed_points(rays, z, L_x, L_d)
-        grads = mlp_backward(params, emb, draw.reshape(-1, 4), D, skips, 3 + 6 * L_x)
+        grads = mlp_backward(params, r[f'emb_{tag}'], draw.reshape(-1, 4), D, skips, 3 + 6 * L_x, acts=r[f'acts_{tag}'])
         out.append((loss, grads))
     return out[0][0], out[1][0], out[0][1], out[1][1]
 
