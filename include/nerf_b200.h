@@ -152,6 +152,11 @@ int nb_mlp_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, co
                     const void* act_save, const float* d_raw, float* grad, int32_t accumulate, int32_t precision,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* Diagnostic (NB_BF16): run the forward chain on rays/z and dump the raw fp32 TMEM accumulators of chain
+ * step `step` (0..9; before bias/activation) to acc_out[N*S,256]; raw_out[N*S,4] as nb_mlp_forward_rays. */
+int nb_mlp_tc_probe(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t N, int32_t S,
+                    const float* rays, const float* z, int32_t step, float* acc_out, float* raw_out, void* stream);
+
 /* ---- K5: compositing -------------------------------------------------------------------- */
 /* nerf_process.py:89-140 post_process: raw[N,S,4], z[N,S], rays_d[N,3] -> rgb[N,3], disp[N], acc[N],
  * weights[N,S], depth[N].  Any output except rgb may be NULL. */

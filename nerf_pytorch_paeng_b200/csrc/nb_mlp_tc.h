@@ -1,0 +1,25 @@
+// Shared between the forward (nb_mlp_tc.cu) and backward (nb_mlp_tc_bwd.cu) tensor-core MLP kernels.
+#pragma once
+#include <functional>
+#include "nb_mlp.h"
+
+constexpr uint32_t kBlobBytes = 16384;   // one K-block of a 128-point tile: 128 rows x 64 bf16, 128B-swizzled
+constexpr int kFwdSteps = 10;
+
+// Activation stash written by the training forward: per tensor, per tile, consecutive 16 KB blobs
+// (the exact shared-memory image, so backward kernels bulk-load them straight into UMMA operands).
+struct TcStash {
+  size_t off_embx, off_embd;   // PE(x) 63(+1.0 pad) cols, PE(d) 27(+1.0 pad) cols : 1 blob / tile
+  size_t off_h[8];             // post-ReLU trunk outputs h0..h7                   : 4 blobs / tile
+  size_t off_feat;             // feature layer output                             : 4 blobs / tile
+  size_t off_g;                // post-ReLU view layer output (128 wide)           : 2 blobs / tile
+  size_t total;
+  long long tiles;
+};
+TcStash nb_tc_stash_layout(long long P);
+
+size_t nb_tc_fwd_packed_bytes();
+size_t nb_tc_bwd_packed_bytes();
+size_t nb_tc_bwd_ws_bytes(const nb_mlp_desc& d, long long P);
+// appends the dgrad (W^T) blobs in consumption order: add(src_float_off, ld, transposed, n0, k0, rows, n_lim, k_lim)
+void nb_tc_bwd_add_blobs(const NbParamLayout& L, const std::function<void(size_t, int, int, int, int, int, int, int)>& add);

@@ -201,6 +201,16 @@ class Engine:
         self._call('nb_mlp_backward', C.byref(desc), _ptr(params), _ptr(packed), n_pts, _ptr(act), _ptr(d_raw), _ptr(grad),
                    1 if accumulate else 0, precision, _ptr(ws), ws.numel(), self.stream)
 
+    def mlp_tc_probe(self, desc, params, packed, rays, z, step):
+        """Diagnostic: fp32 TMEM accumulators of chain step `step` ([P,256]) and raw [P,4]."""
+        rays = _chk32(rays, 'rays')
+        z = _chk32(z, 'z_vals')
+        acc = torch.zeros(z.numel(), 256, device=self.device)
+        raw = self.empty(z.numel(), 4)
+        self._call('nb_mlp_tc_probe', C.byref(desc), _ptr(params), _ptr(packed), z.shape[0], z.shape[1], _ptr(rays), _ptr(z),
+                   int(step), _ptr(acc), _ptr(raw), self.stream)
+        return acc, raw
+
     # ------------------------------------------------------------------ K5
     def composite_forward(self, raw, z, rays_d, want_all=True):
         raw = _chk32(raw, 'outputs')
