@@ -311,7 +311,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', type=str, default=os.environ.get('NB_PRECISION', 'fp32'), choices=['fp32', 'bf16'])
+    ap.add_argument('--precision', type=str, default=os.environ.get('NB_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
     ap.add_argument('--cpu-rays', dest='cpu_rays', type=int, default=256)
     ap.add_argument('--no-cpu', dest='no_cpu', action='store_true')
     args = ap.parse_args()

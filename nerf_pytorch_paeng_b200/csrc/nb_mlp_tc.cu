@@ -101,7 +101,7 @@ __device__ __forceinline__ void pe_row_to_smem(uint32_t row_addr, uint32_t r, fl
       e[3 + 6 * k + 3 + d] = __cosf(a);
     }
   }
-  if (one_pad) e[NF] = 1.0f;                  // constant-one column: its weight-gradient row is the bias gradient
+  if (one_pad) e[NF] = 1.0f;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
@@ -245,10 +245,10 @@ mlp_fwd_chain_kernel(const FwdParams p) {
         const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
         dirx = dx * inv; diry = dy * inv; dirz = dz * inv;
         if (TRAIN && store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, 128); store_pending = false; }
-        pe_row_to_smem<10>(aux_base + r * 128u, r, fmaf(dx, zz, ox), fmaf(dy, zz, oy), fmaf(dz, zz, oz), true);
+        pe_row_to_smem<10>(aux_base + r * 128u, r, fmaf(dx, zz, ox), fmaf(dy, zz, oy), fmaf(dz, zz, oz), false);
       } else {
         if (TRAIN && store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, 128); store_pending = false; }
-        emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x, 63, true);
+        emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x, 63, false);
       }
       fence_proxy_async_smem();
       if (TRAIN) {
@@ -279,6 +279,13 @@ mlp_fwd_chain_kernel(const FwdParams p) {
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c32 * 32) + j4);
             v[j4 * 4 + 0] += b4.x; v[j4 * 4 + 1] += b4.y; v[j4 * 4 + 2] += b4.z; v[j4 * 4 + 3] += b4.w;
+          }
+          if (TRAIN && s != 8) {   // ReLU mask of this layer's output for the backward chain (bit j = column c32*32+j > 0)
+            uint32_t m = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m |= (v[j] > 0.f) ? (1u << j) : 0u;
+            const int layer = s < 8 ? s : 8;
+            reinterpret_cast<uint32_t*>(p.stash + p.st.off_mask)[(((size_t)tile * 9 + layer) * 128 + r) * 8 + c32] = m;
           }
           if (s == 7) {           // sigma head on the fp32 post-ReLU trunk output (NeRF.py:43)
 #pragma unroll
@@ -321,8 +328,8 @@ mlp_fwd_chain_kernel(const FwdParams p) {
         }
         if (s == 5) {
           // the step-9 operand needs PE(viewdir) in aux; aux (PE of the point) was last read by MMA step 5, now retired
-          if (p.x_emb == nullptr) pe_row_to_smem<4>(aux_base + r * 128u, r, dirx, diry, dirz, true);
-          else emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x + 63, 27, true);
+          if (p.x_emb == nullptr) pe_row_to_smem<4>(aux_base + r * 128u, r, dirx, diry, dirz, false);
+          else emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x + 63, 27, false);
         }
         fence_proxy_async_smem();
         tc_fence_before();
@@ -415,6 +422,7 @@ TcStash nb_tc_stash_layout(long long P) {
   for (int i = 0; i < 8; ++i) { s.off_h[i] = off; off += T * 4 * kBlobBytes; }
   s.off_feat = off; off += T * 4 * kBlobBytes;
   s.off_g = off; off += T * 2 * kBlobBytes;
+  s.off_mask = off; off += T * kMaskTileBytes;
   s.total = off;
   s.tiles = (long long)T;
   return s;

@@ -5,6 +5,7 @@
 
 constexpr uint32_t kBlobBytes = 16384;   // one K-block of a 128-point tile: 128 rows x 64 bf16, 128B-swizzled
 constexpr int kFwdSteps = 10;
+constexpr uint32_t kMaskTileBytes = 9 * 128 * 32;   // per tile
 
 // Activation stash written by the training forward: per tensor, per tile, consecutive 16 KB blobs
 // (the exact shared-memory image, so backward kernels bulk-load them straight into UMMA operands).
@@ -13,6 +14,7 @@ struct TcStash {
   size_t off_h[8];             // post-ReLU trunk outputs h0..h7                   : 4 blobs / tile
   size_t off_feat;             // feature layer output                             : 4 blobs / tile
   size_t off_g;                // post-ReLU view layer output (128 wide)           : 2 blobs / tile
+  size_t off_mask;             // ReLU masks: [tile][9 = h0..h7, g][128 rows][8 x u32], bit j of word c = column 32c+j > 0
   size_t total;
   long long tiles;
 };

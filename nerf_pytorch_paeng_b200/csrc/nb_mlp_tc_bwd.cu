@@ -1,8 +1,522 @@
-// K4 backward, NB_BF16 precision (dgrad chain + wgrad).  (placeholder until the kernels land)
+// K4 backward, NB_BF16 precision: autograd of model/NeRF.py:33-52 wrt the parameters (train.py:69).
+//
+// Two kernels per network:
+//  (1) dgrad chain  -- same structure as the forward chain (nb_mlp_tc.cu): per 128-point tile the gradient
+//      wrt each layer's pre-activation is produced by a chain of tcgen05 GEMMs  dY_l = (dY_{l+1} . W_{l+1}) * relu'(h_l)
+//      with dY living in shared memory / TMEM; the ReLU masks come from the forward's activation stash, and
+//      every dY tile is bulk-stored to HBM as swizzled blobs for (2).  Steps per tile:
+//        prologue  dg = (d_rgb . Wc) * (g > 0)                     (CUDA cores, K=3)
+//        0: dfeat = dg . Wd[:, :256]        1: dh7 = (dfeat . Wf + dsigma (x) Wsigma) * (h7 > 0)
+//        2..8: dh_{l-1} = (dh_l . W_l[:, skip cols]) * (h_{l-1} > 0)   for l = 7..1
+//  (2) wgrad -- dW_l = dY_l^T . X_l reduced over all points.  The stashed blobs ([128 points x 64 features],
+//      128B-swizzled) are exactly UMMA "MN-major" operands, so both A = dY_l and B = X_l are bulk-loaded and fed
+//      to tcgen05.mma without any transposition; the 256x256 fp32 accumulator of one weight matrix fills the
+//      512 TMEM columns.  The 14 (layer, input-block) jobs run concurrently on disjoint groups of CTAs sized by
+//      their HBM traffic; bias gradients are column sums of the dY tiles taken from shared memory by spare
+//      warps; results are added to the flat fp32 gradient with red.global.add.
 #include "nb_mlp_tc.h"
+#include "nb_tc_common.cuh"
 
-size_t nb_tc_bwd_packed_bytes() { return 0; }
-size_t nb_tc_bwd_ws_bytes(const nb_mlp_desc&, long long) { return 256; }
-void nb_tc_bwd_add_blobs(const NbParamLayout&, const std::function<void(size_t, int, int, int, int, int, int, int)>&) {}
-int nb_tc_backward(nb_handle_t h, const nb_mlp_desc*, const float*, const void*, int64_t, const void*, const float*, float*,
-                   int, void*, size_t, cudaStream_t) { NB_SET_ERR(h, "bf16 backward not built"); return NB_ERR_UNSUPPORTED; }
+using namespace tc;
+
+namespace {
+
+constexpr int kBwdSteps = 9;
+__host__ __device__ constexpr int bwd_nkb(int b) { return b == 0 ? 2 : 4; }
+__host__ __device__ constexpr uint32_t bwd_w_off(int b) {
+  uint32_t o = 0;
+  for (int i = 0; i < b; ++i) o += (uint32_t)bwd_nkb(i) * 32768u;
+  return o;
+}
+
+// workspace: dY blobs per tile
+struct BwdWs {
+  size_t off_draw;     // [T][2]  d_raw (cols 0..3) as a blob, stored twice: A operand (M=128) of the head wgrad jobs
+  size_t off_dg;       // [T][2]
+  size_t off_dfeat;    // [T][4]
+  size_t off_dh[8];    // [T][4]  dh0..dh7
+  size_t total;
+};
+BwdWs bwd_ws_layout(long long P) {
+  BwdWs w;
+  const size_t T = (size_t)((P + 127) / 128);
+  size_t off = 0;
+  w.off_draw = off; off += T * 2 * kBlobBytes;
+  w.off_dg = off; off += T * 2 * kBlobBytes;
+  w.off_dfeat = off; off += T * 4 * kBlobBytes;
+  for (int i = 0; i < 8; ++i) { w.off_dh[i] = off; off += T * 4 * kBlobBytes; }
+  w.total = off;
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------
+// (1) dgrad chain
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kActBytes = 4 * kBlobBytes;
+constexpr uint32_t kOffAct = 0;
+constexpr uint32_t kOffAux = 2 * kActBytes;
+constexpr uint32_t kOffW = kOffAux + 2 * kBlobBytes;
+constexpr uint32_t kOffBar = kOffW + 2 * 32768;
+constexpr uint32_t kOffWc = kOffBar + 256;
+constexpr uint32_t kSmemBytes = kOffWc + 1536 + 1024;
+constexpr int kThreads = 320;
+
+struct DgradParams {
+  long long P;
+  const uint8_t* wpk;       // packed dgrad blobs (W^T)
+  const float* prm;
+  NbParamLayout L;
+  const float* d_raw;       // [P,4]
+  const uint8_t* stash;     // forward activations
+  TcStash st;
+  uint8_t* ws;              // dY blobs out
+  BwdWs w;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_dgrad_chain_kernel(const DgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_act = sbase + kOffAct, s_aux = sbase + kOffAux, s_w = sbase + kOffW, s_bar = sbase + kOffBar;
+  const uint32_t b_wfull = s_bar, b_wempty = s_bar + 16, b_aready = s_bar + 32, b_accready = s_bar + 48, s_tmem = s_bar + 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n_tiles = (p.P + 127) / 128;
+  const long long tile_stride = 2LL * gridDim.x;
+  auto tile_of = [&](int slot, long long it) { return 2LL * blockIdx.x + slot + it * tile_stride; };
+  const long long max_it = (n_tiles + tile_stride - 1) / tile_stride;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(b_wfull + 8 * i, 1);
+      mbar_init(b_wempty + 8 * i, 1);
+      mbar_init(b_aready + 8 * i, 128);
+      mbar_init(b_accready + 8 * i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(s_tmem, 512);
+  float* s_wc = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + kOffWc);
+  for (int i = threadIdx.x; i < 384; i += kThreads) s_wc[i] = p.prm[p.L.wc + i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (long long it = 0; it < max_it; ++it) {
+#pragma unroll 1
+        for (int b = 0; b < kBwdSteps; ++b) {
+          const uint8_t* src = p.wpk + bwd_w_off(b);
+          for (int slot = 0; slot < 2; ++slot) {
+            if (tile_of(slot, it) >= n_tiles) continue;
+            for (int kb = 0; kb < bwd_nkb(b); ++kb) {
+              mbar_wait(b_wempty + 8 * stage, phase ^ 1);
+              mbar_expect_tx(b_wfull + 8 * stage, 32768u);
+              bulk_g2s(s_w + stage * 32768u, src + (size_t)kb * 32768u, 32768u, b_wfull + 8 * stage);
+              stage ^= 1; if (stage == 0) phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    uint32_t stage = 0, phase = 0, par_a[2] = {0, 0};
+    const uint32_t idesc = umma_idesc(128, 256, 0, 0);
+    for (long long it = 0; it < max_it; ++it) {
+#pragma unroll 1
+      for (int b = 0; b < kBwdSteps; ++b) {
+        for (int slot = 0; slot < 2; ++slot) {
+          if (tile_of(slot, it) >= n_tiles) continue;
+          mbar_wait(b_aready + 8 * slot, par_a[slot]); par_a[slot] ^= 1;
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
+          for (int kb = 0; kb < bwd_nkb(b); ++kb) {
+            mbar_wait(b_wfull + 8 * stage, phase);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_addr = s_act + slot * kActBytes + (uint32_t)kb * kBlobBytes;
+              const uint32_t b_addr = s_w + stage * 32768u;
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                umma_ss(d_tmem, umma_desc(a_addr + k4 * 32u, 16, 1024), umma_desc(b_addr + k4 * 32u, 16, 1024), idesc,
+                        (kb | k4) ? 1u : 0u);
+              umma_commit(b_wempty + 8 * stage);
+              if (kb == bwd_nkb(b) - 1) umma_commit(b_accready + 8 * slot);
+            }
+            __syncwarp();
+            stage ^= 1; if (stage == 0) phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    const int slot = (warp - 2) >> 2;
+    const uint32_t q = (uint32_t)warp & 3u;
+    const uint32_t r = q * 32u + (uint32_t)lane;
+    const uint32_t act_base = s_act + slot * kActBytes, aux_base = s_aux + slot * kBlobBytes;
+    const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + (uint32_t)slot * 256u;
+    const int grp_tid = threadIdx.x - (64 + slot * 128);
+    const int bar_id = 1 + slot;
+    uint32_t par_acc = 0;
+    bool store_pending = false;
+    const float* prm = p.prm;
+
+    for (long long it = 0; it < max_it; ++it) {
+      const long long tile = tile_of(slot, it);
+      if (tile >= n_tiles) break;
+      const long long pt = tile * 128 + r;
+      const bool valid = pt < p.P;
+      // ---- prologue: dg = (d_rgb . Wc) * (g > 0) -> act K-blocks 0,1 ; d_raw blob -> aux ----
+      float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) dr = __ldg(reinterpret_cast<const float4*>(p.d_raw) + pt);   // padded rows carry zero gradient
+      const uint32_t* mrow = reinterpret_cast<const uint32_t*>(p.stash + p.st.off_mask) + ((size_t)tile * 9 * 128 + r) * 8;
+      const uint4 gm = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)8 * 128 * 8));       // mask of g (128 columns)
+      const uint32_t gmw[4] = {gm.x, gm.y, gm.z, gm.w};
+      if (store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, 128); store_pending = false; }
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int col = c * 8 + j;
+          const float val = fmaf(dr.x, s_wc[col], fmaf(dr.y, s_wc[128 + col], dr.z * s_wc[256 + col]));
+          v[j] = ((gmw[col >> 5] >> (col & 31)) & 1u) ? val : 0.f;
+        }
+        st_shared_v4(act_base + (uint32_t)(c >> 3) * kBlobBytes + sw128_chunk(r, (uint32_t)(c & 7)), pack_bf16(v[0], v[1]),
+                     pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t w0 = 0, w1 = 0;
+        if (c == 0) { w0 = pack_bf16(dr.x, dr.y); w1 = pack_bf16(dr.z, dr.w); }
+        st_shared_v4(aux_base + sw128_chunk(r, (uint32_t)c), w0, w1, 0u, 0u);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(bar_id, 128);
+      if (grp_tid == 0) {
+        bulk_s2g(p.ws + p.w.off_dg + (size_t)tile * 2 * kBlobBytes, act_base, 2 * kBlobBytes);
+        bulk_s2g(p.ws + p.w.off_draw + (size_t)tile * 2 * kBlobBytes, aux_base, kBlobBytes);
+        bulk_s2g(p.ws + p.w.off_draw + (size_t)tile * 2 * kBlobBytes + kBlobBytes, aux_base, kBlobBytes);
+        bulk_commit();
+      }
+      store_pending = true;
+      mbar_arrive(b_aready + 8 * slot);
+
+#pragma unroll 1
+      for (int b = 0; b < kBwdSteps; ++b) {
+        // ReLU mask of h_{8-b} for this step (b >= 1): 8 words per row, fetched while the MMA runs
+        uint32_t mq[8] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
+        if (b >= 1) {
+          const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)(8 - b) * 128 * 8));
+          const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)(8 - b) * 128 * 8) + 1);
+          mq[0] = m0.x; mq[1] = m0.y; mq[2] = m0.z; mq[3] = m0.w; mq[4] = m1.x; mq[5] = m1.y; mq[6] = m1.z; mq[7] = m1.w;
+        }
+        mbar_wait(b_accready + 8 * slot, par_acc); par_acc ^= 1;
+        tc_fence_after();
+        if (store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, 128); store_pending = false; }
+#pragma unroll
+        for (int c32 = 0; c32 < 8; ++c32) {
+          float v[32];
+          tmem_ld32(t_addr + (uint32_t)c32 * 32u, v);
+          tmem_ld_wait();
+          if (b == 1) {   // density head: d h7 += d sigma * W_sigma   (NeRF.py:43)
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(prm + p.L.ws + c32 * 32) + j4);
+              v[j4 * 4 + 0] = fmaf(dr.w, w4.x, v[j4 * 4 + 0]); v[j4 * 4 + 1] = fmaf(dr.w, w4.y, v[j4 * 4 + 1]);
+              v[j4 * 4 + 2] = fmaf(dr.w, w4.z, v[j4 * 4 + 2]); v[j4 * 4 + 3] = fmaf(dr.w, w4.w, v[j4 * 4 + 3]);
+            }
+          }
+          {
+            const uint32_t m = mq[c32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (!((m >> j) & 1u)) v[j] = 0.f;
+          }
+          const uint32_t row_addr = act_base + (uint32_t)(c32 >> 1) * kBlobBytes + r * 128u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t c = (uint32_t)((c32 & 1) * 4 + j);
+            st_shared_v4(row_addr + ((c ^ (r & 7u)) << 4), pack_bf16(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16(v[j * 8 + 2], v[j * 8 + 3]),
+                         pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        named_bar_sync(bar_id, 128);
+        if (grp_tid == 0) {
+          const size_t off = (b == 0) ? p.w.off_dfeat : p.w.off_dh[8 - b];
+          bulk_s2g(p.ws + off + (size_t)tile * 4 * kBlobBytes, act_base, 4 * kBlobBytes);
+          bulk_commit();
+        }
+        store_pending = true;
+        if (b < kBwdSteps - 1) mbar_arrive(b_aready + 8 * slot);
+      }
+    }
+    if (store_pending && grp_tid == 0) bulk_wait_all0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// (2) wgrad
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxJobs = 16;
+struct WgradJob {
+  const uint8_t* a;      // dY blobs, [T][a_blobs] (uses the first m_blk of them, offset a_first)
+  const uint8_t* b;      // X blobs,  [T][b_blobs]
+  int a_blobs, a_first, m_blk;    // M = 64*m_blk (2 or 4)
+  int b_blobs, b_first, n_blk;    // N = 64*n_blk (1, 2 or 4)
+  float* out;            // dW + column offset, row-major [rows, ld]
+  int ld, m_first, m_valid, n_valid;   // rows [m_first, m_valid) x cols [0, n_valid) are written; row m -> out + (m - m_first)*ld
+  float* bias_out;       // dY column sums of columns [m_first, m_valid) or nullptr
+  int cta_begin, cta_count;
+};
+struct WgradParams { WgradJob job[kMaxJobs]; int n_jobs; long long n_tiles; };
+
+constexpr int kWgThreads = 192;                         // warp0 producer, warp1 MMA, warps 2-5 bias sums + epilogue
+constexpr int kWgStages = 3;
+constexpr uint32_t kWgStageBytes = 8 * 8192;            // up to 4 A + 4 B half-blobs (64 points x 128 B)
+constexpr uint32_t kWgOffBar = kWgStages * kWgStageBytes;
+constexpr uint32_t kWgSmemBytes = kWgOffBar + 256 + 1024;
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+mlp_wgrad_kernel(const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_bar = sbase + kWgOffBar;
+  const uint32_t b_full = s_bar, b_empty = s_bar + 32, b_done = s_bar + 64, s_tmem = s_bar + 72;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // which job does this CTA work on
+  int ji = -1;
+  for (int j = 0; j < p.n_jobs; ++j)
+    if ((int)blockIdx.x >= p.job[j].cta_begin && (int)blockIdx.x < p.job[j].cta_begin + p.job[j].cta_count) ji = j;
+  if (ji < 0) return;
+  const WgradJob& J = p.job[ji];
+  const int rank = (int)blockIdx.x - J.cta_begin;
+  // units of work: half tiles (64 points); unit u -> tile u>>1, half u&1
+  const long long n_units = p.n_tiles * 2;
+  const long long my_units = (n_units > rank) ? (n_units - rank + J.cta_count - 1) / J.cta_count : 0;
+  const uint32_t stage_bytes = (uint32_t)(J.m_blk + J.n_blk) * 8192u;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgStages; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1 + 4); }
+    mbar_init(b_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (long long i = 0; i < my_units; ++i) {
+        const long long u = rank + i * J.cta_count;
+        const long long tile = u >> 1;
+        const uint32_t half = (uint32_t)(u & 1) * 8192u;
+        mbar_wait(b_empty + 8 * stage, phase ^ 1);
+        mbar_expect_tx(b_full + 8 * stage, stage_bytes);
+        const uint32_t dst = sbase + stage * kWgStageBytes;
+        for (int k = 0; k < J.m_blk; ++k)
+          bulk_g2s(dst + (uint32_t)k * 8192u, J.a + ((size_t)tile * J.a_blobs + J.a_first + k) * kBlobBytes + half, 8192u, b_full + 8 * stage);
+        for (int k = 0; k < J.n_blk; ++k)
+          bulk_g2s(dst + (uint32_t)(J.m_blk + k) * 8192u, J.b + ((size_t)tile * J.b_blobs + J.b_first + k) * kBlobBytes + half, 8192u,
+                   b_full + 8 * stage);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    uint32_t stage = 0, phase = 0;
+    const uint32_t idesc = umma_idesc(128, 64 * J.n_blk, 1, 1);      // both operands MN-major
+    const int m_halves = J.m_blk >> 1;
+    for (long long i = 0; i < my_units; ++i) {
+      mbar_wait(b_full + 8 * stage, phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = sbase + stage * kWgStageBytes;
+        const uint32_t b_addr = a_addr + (uint32_t)J.m_blk * 8192u;
+        for (int mh = 0; mh < m_halves; ++mh) {
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16)      // 64 points per stage = 4 x K16
+            umma_ss(tmem_base + (uint32_t)mh * 256u, umma_desc(a_addr + (uint32_t)mh * 16384u + k16 * 2048u, 8192, 1024),
+                    umma_desc(b_addr + k16 * 2048u, 8192, 1024), idesc, (i | k16) ? 1u : 0u);
+        }
+        umma_commit(b_empty + 8 * stage);
+        if (i == my_units - 1) umma_commit(b_done);
+      }
+      __syncwarp();
+      if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+    }
+    if (my_units == 0 && lane == 0) mbar_arrive(b_done);
+  } else {
+    // ---- bias column sums from the A stages, then the TMEM -> global epilogue ----
+    const int t = threadIdx.x - 64;          // 0..127: columns 2t, 2t+1 of the dY tile (M = 64*m_blk <= 256)
+    const bool has_col = (2 * t) < 64 * J.m_blk;
+    float bs0 = 0.f, bs1 = 0.f;
+    uint32_t stage = 0, phase = 0;
+    for (long long i = 0; i < my_units; ++i) {
+      mbar_wait(b_full + 8 * stage, phase);
+      if (J.bias_out != nullptr && has_col) {
+        // column pair 2t,2t+1 lives in blob (2t)/64, 16B-chunk ((2t)%64)/8, word ((2t)%8)/2 of every 128-byte row
+        const int blob = (2 * t) >> 6, cc = ((2 * t) & 63) >> 3, wd = ((2 * t) & 7) >> 1;
+        const uint32_t base = sbase + stage * kWgStageBytes + (uint32_t)blob * 8192u;
+#pragma unroll 8
+        for (uint32_t row = 0; row < 64; ++row) {
+          uint32_t w;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + sw128_chunk(row, (uint32_t)cc) + (uint32_t)wd * 4u));
+          bs0 += __uint_as_float(w << 16);
+          bs1 += __uint_as_float(w & 0xFFFF0000u);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_empty + 8 * stage);
+      if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+    }
+    if (J.bias_out != nullptr && has_col && my_units > 0) {
+      if (2 * t >= J.m_first && 2 * t < J.m_valid) atomicAdd(J.bias_out + 2 * t - J.m_first, bs0);
+      if (2 * t + 1 >= J.m_first && 2 * t + 1 < J.m_valid) atomicAdd(J.bias_out + 2 * t + 1 - J.m_first, bs1);
+    }
+    // accumulators -> flat gradient
+    mbar_wait(b_done, 0);
+    tc_fence_after();
+    if (my_units > 0) {
+      const uint32_t q = (uint32_t)warp & 3u;
+      const int m_halves = J.m_blk >> 1;
+      for (int mh = 0; mh < m_halves; ++mh) {
+        const int m = mh * 128 + (int)(q * 32u) + lane;          // output row (out-feature)
+        for (int c32 = 0; c32 < 2 * J.n_blk; ++c32) {
+          float v[32];
+          tmem_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)mh * 256u + (uint32_t)c32 * 32u, v);
+          tmem_ld_wait();
+          if (m >= J.m_first && m < J.m_valid) {
+            float* dst = J.out + (size_t)(m - J.m_first) * J.ld + c32 * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c32 * 32 + j < J.n_valid) atomicAdd(dst + j, v[j]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+size_t nb_tc_bwd_packed_bytes() { return bwd_w_off(kBwdSteps); }
+size_t nb_tc_bwd_ws_bytes(const nb_mlp_desc&, long long P) { return bwd_ws_layout(P).total + 256; }
+
+void nb_tc_bwd_add_blobs(const NbParamLayout& L, const std::function<void(size_t, int, int, int, int, int, int, int)>& add) {
+  // blob[n][k] = W[k0+k][n0+n]  (B = W^T, rows = in-features, K = out-features)
+  for (int kb = 0; kb < 2; ++kb) add(L.wd, 283, 1, 0, 64 * kb, 256, 256, 128);              // step 0: Wd[:, :256]
+  for (int kb = 0; kb < 4; ++kb) add(L.wf, 256, 1, 0, 64 * kb, 256, 256, 256);              // step 1: Wf
+  const int layers[7] = {7, 6, 5, 4, 3, 2, 1};                                              // steps 2..8
+  for (int i = 0; i < 7; ++i) {
+    const int l = layers[i];
+    const size_t src = L.w[l] + (l == 5 ? 63 : 0);                                           // skip layer: the h columns of W5
+    for (int kb = 0; kb < 4; ++kb) add(src, L.in_dim[l], 1, 0, 64 * kb, 256, 256, 256);
+  }
+}
+
+int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t P,
+                   const void* act_save, const float* d_raw, float* grad, int accumulate, void* ws, size_t ws_bytes,
+                   cudaStream_t st) {
+  const NbParamLayout L = nb_param_layout(*d);
+  const BwdWs W = bwd_ws_layout(P);
+  if (!ws || ws_bytes < W.total) {
+    NB_SET_ERR(h, "mlp bf16 backward: workspace %zu < %zu bytes", ws_bytes, W.total);
+    return NB_ERR_WORKSPACE;
+  }
+  NB_REQUIRE(h, ((uintptr_t)d_raw & 15) == 0 && ((uintptr_t)ws & 15) == 0 && ((uintptr_t)act_save & 15) == 0,
+             "mlp bf16 backward: d_raw / act_save / ws must be 16-byte aligned");
+  if (!accumulate) NB_CUDA(h, cudaMemsetAsync(grad, 0, L.total * sizeof(float), st));
+  const TcStash S = nb_tc_stash_layout(P);
+  const long long n_tiles = S.tiles;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NB_CUDA(h, cudaFuncSetAttribute(mlp_dgrad_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    NB_CUDA(h, cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemBytes));
+    attr_done = true;
+  }
+  // ---- (1) dgrad chain
+  {
+    DgradParams dp;
+    memset(&dp, 0, sizeof(dp));
+    dp.P = P; dp.wpk = (const uint8_t*)packed + nb_tc_fwd_packed_bytes(); dp.prm = params; dp.L = L; dp.d_raw = d_raw;
+    dp.stash = (const uint8_t*)act_save; dp.st = S; dp.ws = (uint8_t*)ws; dp.w = W;
+    long long grid = (n_tiles + 1) / 2;
+    if (grid > h->sm_count) grid = h->sm_count;
+    mlp_dgrad_chain_kernel<<<(int)grid, kThreads, kSmemBytes, st>>>(dp);
+    NB_LAUNCHED(h);
+  }
+  // ---- (2) wgrad jobs
+  {
+    WgradParams wp;
+    memset(&wp, 0, sizeof(wp));
+    wp.n_tiles = n_tiles;
+    const uint8_t* stash = (const uint8_t*)act_save;
+    const uint8_t* w8 = (const uint8_t*)ws;
+    int weight[kMaxJobs];
+    int nj = 0;
+    auto add = [&](const uint8_t* a, int a_blobs, int a_first, int m_blk, const uint8_t* b, int b_blobs, int b_first, int n_blk,
+                   float* out, int ld, int m_first, int m_valid, int n_valid, float* bias) {
+      WgradJob& j = wp.job[nj];
+      j.a = a; j.a_blobs = a_blobs; j.a_first = a_first; j.m_blk = m_blk; j.b = b; j.b_blobs = b_blobs; j.b_first = b_first;
+      j.n_blk = n_blk; j.out = out; j.ld = ld; j.m_first = m_first; j.m_valid = m_valid; j.n_valid = n_valid; j.bias_out = bias;
+      weight[nj] = m_blk + n_blk;       // HBM bytes per point ~ blobs loaded
+      ++nj;
+    };
+    const uint8_t* dh[8];
+    for (int i = 0; i < 8; ++i) dh[i] = w8 + W.off_dh[i];
+    // trunk layers
+    add(dh[0], 4, 0, 4, stash + S.off_embx, 1, 0, 1, grad + L.w[0], 63, 0, 256, 63, grad + L.b[0]);
+    for (int l = 1; l < 8; ++l) {
+      if (l == 5) {
+        add(dh[5], 4, 0, 4, stash + S.off_embx, 1, 0, 1, grad + L.w[5], 319, 0, 256, 63, grad + L.b[5]);
+        add(dh[5], 4, 0, 4, stash + S.off_h[4], 4, 0, 4, grad + L.w[5] + 63, 319, 0, 256, 256, nullptr);
+      } else {
+        add(dh[l], 4, 0, 4, stash + S.off_h[l - 1], 4, 0, 4, grad + L.w[l], 256, 0, 256, 256, grad + L.b[l]);
+      }
+    }
+    // feature layer, view layer, heads
+    add(w8 + W.off_dfeat, 4, 0, 4, stash + S.off_h[7], 4, 0, 4, grad + L.wf, 256, 0, 256, 256, grad + L.bf);
+    add(w8 + W.off_dg, 2, 0, 2, stash + S.off_feat, 4, 0, 4, grad + L.wd, 283, 0, 128, 256, grad + L.bd);
+    add(w8 + W.off_dg, 2, 0, 2, stash + S.off_embd, 1, 0, 1, grad + L.wd + 256, 283, 0, 128, 27, nullptr);
+    // heads: A = d_raw blob (cols 0..2 = d_rgb, col 3 = d_sigma), stored twice so that M = 128 is addressable
+    add(w8 + W.off_draw, 2, 0, 2, stash + S.off_g, 2, 0, 2, grad + L.wc, 128, 0, 3, 128, grad + L.bc);          // dWc, dbc
+    add(w8 + W.off_draw, 2, 0, 2, stash + S.off_h[7], 4, 0, 4, grad + L.ws, 256, 3, 4, 256, grad + L.bs);       // dWsigma, dbsigma
+    wp.n_jobs = nj;
+    // distribute the CTAs over jobs proportionally to their traffic
+    int total_w = 0;
+    for (int j = 0; j < nj; ++j) total_w += weight[j];
+    int n_cta = h->sm_count;
+    int given = 0;
+    for (int j = 0; j < nj; ++j) {
+      int c = (int)((long long)weight[j] * n_cta / total_w);
+      if (c < 1) c = 1;
+      wp.job[j].cta_count = c;
+      given += c;
+    }
+    for (int j = 0; given < n_cta; j = (j + 1) % nj) { wp.job[j].cta_count++; given++; }
+    int begin = 0;
+    for (int j = 0; j < nj; ++j) { wp.job[j].cta_begin = begin; begin += wp.job[j].cta_count; }
+    mlp_wgrad_kernel<<<begin, kWgThreads, kWgSmemBytes, st>>>(wp);
+    NB_LAUNCHED(h);
+  }
+  return NB_OK;
+}
