@@ -176,7 +176,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).to(dev)      # random init, identical on every rank
     model.set_precision(args.precision)
-    opts = make_opts(rank_dev=local, seed=1000 + rank)
+    opts = make_opts(rank_dev=local, seed=1000 + rank, device_select=True)
     optimizer = trainer.FlatAdam(model, lr=5e-4)
     posenc = [get_positional_encoder(10)[0], get_positional_encoder(4)[0]]
     K = np.array([[FOCAL, 0, 400.], [0, FOCAL, 400.], [0, 0, 1.]])
@@ -222,36 +222,48 @@ def run_ours(args):
     ms_step = float(t) / args.steps
     value = N_RAYS * world / (ms_step / 1e3)
 
-    # ---- roofline of the dominant kernels (the MLP): CUDA events around every MLP call of K steps
-    mlp_ms, mlp_calls = [0.0], [0]
+    # ---- roofline of the dominant kernel: CUDA events (on the launching stream) around every MLP call of a few steps.
+    # engine.mlp_forward == exactly one launch of mlp_fwd_chain_kernel<train> (42% of the step per the ncu launch list);
+    # engine.mlp_backward == cudaMemsetAsync + mlp_dgrad_chain_kernel + mlp_wgrad_kernel.
     of, ob = eng.mlp_forward, eng.mlp_backward
-    pend = []
+    pend = {'fwd': [], 'bwd': []}
 
-    def timed(fn):
+    def timed(fn, tag):
         def wrap(*a, **k):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             r = fn(*a, **k)
             e1.record()
-            pend.append((e0, e1))
-            mlp_calls[0] += 1
+            pend[tag].append((e0, e1))
             return r
         return wrap
-    eng.mlp_forward, eng.mlp_backward = timed(of), timed(ob)
-    lm0 = eng.launch_count()
+    eng.mlp_forward, eng.mlp_backward = timed(of, 'fwd'), timed(ob, 'bwd')
     n_prof = min(args.steps, 5)
     for i in range(n_prof):
         step(i)
     torch.cuda.synchronize()
     eng.mlp_forward, eng.mlp_backward = of, ob
-    mlp_ms = sum(a.elapsed_time(b) for a, b in pend) / n_prof
-    flop_step = FLOP_PER_POINT_TRAIN * N_RAYS * POINTS_PER_RAY
+    fwd_ms = [a.elapsed_time(b) for a, b in pend['fwd']]
+    bwd_ms = [a.elapsed_time(b) for a, b in pend['bwd']]
+    mlp_ms = (sum(fwd_ms) + sum(bwd_ms)) / n_prof
     peak_tf, peak_hbm, peak_src = peaks()
-    achieved = flop_step / (mlp_ms / 1e3) / 1e12
+    pts_per_launch = N_RAYS * POINTS_PER_RAY / 2.0                       # two launches per step: 64- and 192-sample nets
+    fwd_avg_ms = sum(fwd_ms) / len(fwd_ms)
+    achieved = FLOP_PER_POINT_FWD * pts_per_launch / (fwd_avg_ms / 1e3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get('mlp_fwd_chain_kernel_train_bytes_per_launch')
+    flop_step = FLOP_PER_POINT_TRAIN * N_RAYS * POINTS_PER_RAY
+    bwd_tf = (FLOP_PER_POINT_TRAIN - FLOP_PER_POINT_FWD) * pts_per_launch / (sum(bwd_ms) / len(bwd_ms) / 1e3) / 1e12
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
-                'traffic': None, 'kernel': 'MLP forward+backward (4 calls/step: coarse+fine fwd, coarse+fine bwd)',
-                'algorithmic_flop_per_step': flop_step, 'mlp_ms_per_step': mlp_ms, 'mlp_share_of_step': mlp_ms / ms_step,
-                'peak_source': peak_src}
+                'traffic': traffic, 'kernel': 'mlp_fwd_chain_kernel<train> (tcgen05 fused 8x256 MLP forward incl. PE, bf16 stash stores)',
+                'algorithmic_flop_per_launch': FLOP_PER_POINT_FWD * pts_per_launch, 'avg_launch_ms': fwd_avg_ms,
+                'launches_per_step': 2, 'peak_source': peak_src,
+                'other_kernels': {'mlp_backward (dgrad chain + wgrad)': {'achieved_tflops': bwd_tf, 'frac': bwd_tf / peak_tf,
+                                                                          'avg_call_ms': sum(bwd_ms) / len(bwd_ms)}},
+                'whole_step': {'algorithmic_flop_per_step': flop_step, 'mlp_ms_per_step': mlp_ms, 'mlp_share_of_step': mlp_ms / ms_step,
+                               'achieved_tflops': flop_step / (mlp_ms / 1e3) / 1e12, 'frac': flop_step / (mlp_ms / 1e3) / 1e12 / peak_tf}}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: the reference-facing call train.train(...) with HOST inputs every step
@@ -280,9 +292,9 @@ def run_ours(args):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     e2e_ms_step = float(t) / args.steps
     e2e = {'value': N_RAYS * world / (e2e_ms_step / 1e3), 'unit': 'rays/s', 'ms_per_step': e2e_ms_step,
-           'h2d_bytes_per_step': H * W * 3 * 4 + N_RAYS * 8, 'd2h_bytes_per_step': 4,
-           'api': 'nerf_pytorch_paeng_b200.train.train (per-image path, train.py:35-45: pinned host image -> H2D, '
-                  'np.random.choice pixel selection on host, ray-gen + gather + fused step on device, loss D2H)'}
+           'h2d_bytes_per_step': H * W * 3 * 4, 'd2h_bytes_per_step': 4,
+           'api': 'nerf_pytorch_paeng_b200.train.train (per-image path, train.py:35-45: pinned host image -> H2D every step, '
+                  'pixel selection + ray-gen + target gather + fused step + Adam on device, loss D2H)'}
 
     if rank != 0:
         return

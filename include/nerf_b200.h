@@ -100,6 +100,12 @@ int nb_ndc_rays(nb_handle_t h, int64_t N, int32_t H, int32_t W, double focal, do
 int nb_gather_rows(nb_handle_t h, int64_t N, int32_t C, const int64_t* idx, const float* src, float* out,
                    void* stream);
 
+/* rays.py:40-54 pixel selection on the device: N DISTINCT flat pixel indices r*W+c drawn
+ * uniformly from the region rows [r0,r0+nr) x cols [c0,c0+nc) (the whole image, or the precrop window),
+ * out[n] = perm_seed((offset+n) mod nr*nc) with perm a keyed bijection -- no permutation array, no host work. */
+int nb_select_pixels(nb_handle_t h, int64_t N, int32_t H, int32_t W, int32_t r0, int32_t c0, int32_t nr, int32_t nc,
+                     uint64_t seed, uint64_t offset, int64_t* out, void* stream);
+
 /* ---- K2: sampling ---------------------------------------------------------------------- */
 /* nerf_process.py:43-60: z[n,s] = lower[s] + span[s]*t_rand[n,s]  (span = upper-lower, both [S_c],
  * computed once by the caller from torch.linspace).  t_rand NULL => in-kernel Philox4x32-10

@@ -40,6 +40,7 @@ SIGNATURES = {
     'nb_raygen_pinhole': (C.c_int, [_p, _i32, _i32, _f64, _f64, _f64, _f64, _p, _i64, _p, _i64, _p, _p, _u32, _f64, _f64, _p]),
     'nb_ndc_rays': (C.c_int, [_p, _i64, _i32, _i32, _f64, _f64, _p, _p, _p, _p, _p]),
     'nb_gather_rows': (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p]),
+    'nb_select_pixels': (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _u64, _u64, _p, _p]),
     'nb_stratified': (C.c_int, [_p, _i64, _i32, _p, _p, _p, _u64, _u64, _p, _p]),
     'nb_sample_pdf': (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _i32, _u64, _u64, _p, _p, _p, _p, _p, _p, _p]),
     'nb_posenc': (C.c_int, [_p, _i64, _i32, _p, _p, _p]),

@@ -20,6 +20,7 @@
 //
 // In training the bf16 A tiles (layer inputs) are additionally bulk-stored to HBM as 16 KB swizzled blobs
 // which the backward kernels (nb_mlp_tc_bwd.cu) consume directly as UMMA operands.
+#include <stdlib.h>
 #include "nb_mlp.h"
 #include "nb_tc_common.cuh"
 #include "nb_mlp_tc.h"
@@ -74,6 +75,7 @@ struct FwdParams {
   TcStash st;
   float* dbg;             // optional [P,256] accumulator dump of step dbg_step
   int dbg_step;
+  int abl;                // ablation bits for profiling experiments (NB_TC_ABLATE env): 1 no masks, 2 no stash stores
 };
 
 // positional-encoding features of one 3-vector, written as bf16 into a swizzled 128-byte row.
@@ -267,7 +269,10 @@ mlp_fwd_chain_kernel(const FwdParams p) {
         const int ncols = fwd_n(s);
         const float* bias = prm + (s < 8 ? p.L.b[s] : (s == 8 ? p.L.bf : p.L.bd));
         float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-        for (int c32 = 0; c32 < ncols / 32; ++c32) {
+        uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int c32 = 0; c32 < 8; ++c32) {
+          if (c32 * 32 >= ncols) break;
           float v[32];
           tmem_ld32(t_addr + (uint32_t)c32 * 32u, v);
           tmem_ld_wait();
@@ -280,12 +285,11 @@ mlp_fwd_chain_kernel(const FwdParams p) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c32 * 32) + j4);
             v[j4 * 4 + 0] += b4.x; v[j4 * 4 + 1] += b4.y; v[j4 * 4 + 2] += b4.z; v[j4 * 4 + 3] += b4.w;
           }
-          if (TRAIN && s != 8) {   // ReLU mask of this layer's output for the backward chain (bit j = column c32*32+j > 0)
+          if (TRAIN && s != 8 && !(p.abl & 1)) {   // ReLU mask of this layer's output for the backward chain (bit j = column c32*32+j > 0)
             uint32_t m = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) m |= (v[j] > 0.f) ? (1u << j) : 0u;
-            const int layer = s < 8 ? s : 8;
-            reinterpret_cast<uint32_t*>(p.stash + p.st.off_mask)[(((size_t)tile * 9 + layer) * 128 + r) * 8 + c32] = m;
+            mw[c32] = m;
           }
           if (s == 7) {           // sigma head on the fp32 post-ReLU trunk output (NeRF.py:43)
 #pragma unroll
@@ -326,6 +330,12 @@ mlp_fwd_chain_kernel(const FwdParams p) {
             }
           }
         }
+        if (TRAIN && s != 8) {   // 32 contiguous bytes per row: full-sector stores
+          const int layer = s < 8 ? s : 8;
+          uint4* mdst = reinterpret_cast<uint4*>(p.stash + p.st.off_mask) + (((size_t)tile * 9 + layer) * 128 + r) * 2;
+          mdst[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+          mdst[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+        }
         if (s == 5) {
           // the step-9 operand needs PE(viewdir) in aux; aux (PE of the point) was last read by MMA step 5, now retired
           if (p.x_emb == nullptr) pe_row_to_smem<4>(aux_base + r * 128u, r, dirx, diry, dirz, false);
@@ -335,7 +345,7 @@ mlp_fwd_chain_kernel(const FwdParams p) {
         tc_fence_before();
         if (TRAIN) {
           named_bar_sync(bar_id, 128);
-          if (grp_tid == 0) {
+          if (grp_tid == 0 && !(p.abl & 2)) {
             const size_t off = (s < 8 ? p.st.off_h[s] : (s == 8 ? p.st.off_feat : p.st.off_g));
             const uint32_t nb = (s == 9) ? 2u : 4u;
             bulk_s2g(p.stash + off + (size_t)tile * nb * kBlobBytes, act_base, nb * kBlobBytes);
@@ -482,6 +492,7 @@ int nb_tc_forward(nb_handle_t h, const nb_mlp_desc* d, const float* params, cons
   fp.wpk = (const uint8_t*)packed; fp.prm = params; fp.L = nb_param_layout(*d); fp.raw = raw_out;
   fp.stash = (uint8_t*)act_save; fp.st = nb_tc_stash_layout(P);
   fp.dbg = nullptr; fp.dbg_step = -1;
+  { const char* e = getenv("NB_TC_ABLATE"); fp.abl = e ? atoi(e) : 0; }
   return launch_fwd(h, fp, act_save != nullptr, st);
 }
 

@@ -108,6 +108,34 @@ __global__ void gather_rows_kernel(long long N, int C, const long long* __restri
   out[i] = src[idx[n] * C + c];
 }
 
+// Random pixel selection without replacement (rays.py:40-54) with no permutation array:
+// a keyed Feistel network is a bijection on [0, 2^bits); cycle-walking restricts it to [0, D), so distinct
+// counters give distinct pixels.  (The reference draws np.random.choice on the host; only the distribution --
+// a uniformly random subset -- is contractual.)
+__device__ __forceinline__ uint32_t feistel_perm(uint32_t x, int half_bits, uint32_t k0, uint32_t k1) {
+  const uint32_t mask = (1u << half_bits) - 1u;
+  uint32_t l = x >> half_bits, r = x & mask;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t f = (r + k0) * 0x9E3779B1u + (k1 ^ (0x85EBCA6Bu * (uint32_t)(i + 1)));
+    f ^= f >> 15; f *= 0x2C1B3C6Du; f ^= f >> 12;
+    const uint32_t nl = r;
+    r = (l ^ f) & mask;
+    l = nl;
+  }
+  return (l << half_bits) | r;
+}
+
+__global__ void select_pixels_kernel(long long N, int W, int r0, int c0, int nc, uint32_t D, int half_bits, uint32_t k0,
+                                     uint32_t k1, unsigned long long offset, long long* __restrict__ out) {
+  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  uint32_t y = (uint32_t)((offset + (unsigned long long)n) % D);
+  do { y = feistel_perm(y, half_bits, k0, k1); } while (y >= D);
+  const int rr = (int)(y / (uint32_t)nc), cc = (int)(y % (uint32_t)nc);
+  out[n] = (long long)(r0 + rr) * W + (c0 + cc);
+}
+
 NdcConst make_ndc(int H, int W, double focal, double near) {
   NdcConst c;
   c.c_w = (float)(-1. / (W / (2. * focal)));   // evaluated in double, then rounded
@@ -153,6 +181,24 @@ extern "C" int nb_gather_rows(nb_handle_t h, int64_t N, int32_t C, const int64_t
   NB_REQUIRE(h, N >= 0 && C > 0 && idx && src && out, "nb_gather_rows: bad arguments");
   if (N == 0) return NB_OK;
   gather_rows_kernel<<<nb_cdiv(N * C, 256), 256, 0, (cudaStream_t)stream>>>((long long)N, C, (const long long*)idx, src, out);
+  NB_LAUNCHED(h);
+  return NB_OK;
+}
+
+extern "C" int nb_select_pixels(nb_handle_t h, int64_t N, int32_t H, int32_t W, int32_t r0, int32_t c0, int32_t nr, int32_t nc,
+                                uint64_t seed, uint64_t offset, int64_t* out, void* stream) {
+  NB_ENTER(h);
+  if (N == 0) return NB_OK;
+  NB_REQUIRE(h, N > 0 && out && H > 0 && W > 0 && nr > 0 && nc > 0 && r0 >= 0 && c0 >= 0 && r0 + nr <= H && c0 + nc <= W,
+             "nb_select_pixels: bad region");
+  const unsigned long long D = (unsigned long long)nr * nc;
+  NB_REQUIRE(h, (unsigned long long)N <= D && D < (1ull << 31), "nb_select_pixels: N must be <= region size < 2^31");
+  int bits = 2;
+  while ((1ull << bits) < D) ++bits;
+  if (bits & 1) ++bits;
+  select_pixels_kernel<<<nb_cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(
+      (long long)N, W, r0, c0, nc, (uint32_t)D, bits / 2, (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0xA511E9B3u,
+      (unsigned long long)offset, (long long*)out);
   NB_LAUNCHED(h);
   return NB_OK;
 }

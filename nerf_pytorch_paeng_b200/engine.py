@@ -98,6 +98,13 @@ class Engine:
         self._call('nb_gather_rows', idx.numel(), c, _ptr(idx), _ptr(src2), _ptr(out), self.stream)
         return out
 
+    def select_pixels(self, n, H, W, region=None, seed=0, offset=0):
+        """n distinct random flat pixel indices (int64, device) from region=(r0, c0, nr, nc) or the whole image."""
+        r0, c0, nr, nc = region if region is not None else (0, 0, H, W)
+        out = self.empty(n, dtype=torch.int64)
+        self._call('nb_select_pixels', n, H, W, r0, c0, nr, nc, seed, offset, _ptr(out), self.stream)
+        return out
+
     # ------------------------------------------------------------------ K2
     def stratified(self, n_rays, lower, span, t_rand=None, seed=0, offset=0):
         s_c = lower.numel()

@@ -61,7 +61,17 @@ def train(idx, i_train, images, gt_cam_param, hw, model, criterion, posenc, opti
     else:                                                                         # train.py:35-45
         i_img = np.random.choice(i_train)
         pose = _device_copy(gt_extrinsic, device, 'poses')[i_img, :3, :4]
-        pix = torch.from_numpy(select_pixels(idx, img_h, img_w, opts)).to(device, non_blocking=True)
+        if getattr(opts, 'device_select', False):
+            # selection on the device (keyed bijection, distinct pixels, no host permutation)
+            region = None
+            if idx < opts.precrop_iters:
+                dH, dW = int(img_h // 2 * opts.precrop_frac), int(img_w // 2 * opts.precrop_frac)
+                region = (img_h // 2 - dH, img_w // 2 - dW, 2 * dH, 2 * dW)
+            from .engine import get_engine as _ge
+            pix = _ge(device).select_pixels(opts.N_rays, img_h, img_w, region, seed=int(getattr(opts, 'seed', 0)) + 7919 * i_img,
+                                            offset=idx * opts.N_rays)
+        else:
+            pix = torch.from_numpy(select_pixels(idx, img_h, img_w, opts)).to(device, non_blocking=True)
         img = images[i_img]
         img = img if isinstance(img, torch.Tensor) else torch.from_numpy(img)
         img = img.to(device=device, dtype=torch.float32, non_blocking=True)      # H2D of the target image

@@ -114,6 +114,25 @@ def test_sample_rays_and_pixel(eng):
     assert bool((st == 1).all())
 
 
+def test_select_pixels_device(eng):
+    """Device-side selection: distinct, in range, inside the crop window, uniform, different per offset/seed."""
+    H, W = 800, 800
+    a = npy(eng.select_pixels(4096, H, W, seed=3, offset=0))
+    b = npy(eng.select_pixels(4096, H, W, seed=3, offset=4096))
+    c = npy(eng.select_pixels(4096, H, W, seed=4, offset=0))
+    for x in (a, b, c):
+        assert x.min() >= 0 and x.max() < H * W and np.unique(x).size == 4096
+    assert np.intersect1d(a, b).size == 0                 # consecutive offsets walk one permutation: no repeats in an epoch
+    assert np.intersect1d(a, c).size < 200
+    full = npy(eng.select_pixels(H * W, H, W, seed=11, offset=5))
+    assert np.array_equal(np.sort(full), np.arange(H * W))   # a bijection of the whole image
+    rows = a // W
+    assert abs(rows.mean() - (H - 1) / 2) < 15 and abs((a % W).mean() - (W - 1) / 2) < 15
+    crop = npy(eng.select_pixels(1000, H, W, region=(200, 300, 100, 50), seed=1))
+    assert np.unique(crop).size == 1000
+    assert (crop // W).min() >= 200 and (crop // W).max() < 300 and (crop % W).min() >= 300 and (crop % W).max() < 350
+
+
 # ------------------------------------------------------------------------------------------ K3
 def test_posenc(eng):
     g = load_golden('posenc.npz')

@@ -1,0 +1,105 @@
+"""CPU: host-side logic -- config parsing, state_dict compatibility, ray sharding, and the N>1 path
+(world_size 2 over gloo)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, load_golden
+
+
+def test_config_defaults_and_files(tmp_path):
+    from nerf_pytorch_paeng_b200.config import get_args_parser
+    cfg = tmp_path / 'lego.txt'
+    cfg.write_text('# >> Setting\ngpu_ids = [1]\ndata_type = blender\nnear = 2.\nfar = 6.\nbkg_white_true\n'
+                   'global_batch_false\nN_rays = 4096   # rays\nidx_save = 100000\niter_N = 200000\nexp_name = blender_lego\n')
+    o = get_args_parser(['--config', str(cfg)])
+    assert (o.near, o.far, o.gpu_ids, o.world_size, o.rank) == (2., 6., [1], 1, 0)
+    assert o.bkg_white is True and o.global_batch is False
+    # defaults of config.py:54-76
+    assert (o.L_x, o.L_d, o.netDepth, o.netWidth) == (10, 4, 8, 256)
+    assert (o.N_rays, o.N_samples_c, o.N_samples_f, o.chunk_rays, o.chunk_pts) == (4096, 64, 128, 4096, 524288)
+    assert (o.lr, o.lr_min, o.iter_warmup, o.precrop_iters) == (5e-4, 5e-5, 10000, 0)
+    o2 = get_args_parser(['--config', str(cfg), '--N_rays', '1024', '--gpu_ids', '0', '1'])
+    assert o2.N_rays == 1024 and o2.gpu_ids == [0, 1] and o2.world_size == 2
+
+
+def test_state_dict_matches_reference_layout():
+    from nerf_pytorch_paeng_b200.model import NeRF
+    g = load_golden('mlp_w256_seed0.npz')
+    torch.manual_seed(0)
+    net = NeRF(8, 256, 63, 27, [4], gt_camera_param=(np.eye(3), np.zeros((2, 4, 4))))
+    sd = net.state_dict()
+    assert list(sd.keys()) == [str(s) for s in g['param_names']]
+    np.testing.assert_allclose([float(v.double().sum()) for v in sd.values()], g['param_sums'], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose([float(v.flatten()[0]) for v in sd.values()], g['param_first'], rtol=0, atol=0)
+    K, E = net.get_camera_gt()
+    assert K.shape == (3, 3) and E.shape == (2, 4, 4)
+    assert sd['model_coarse.linear_x.5.weight'].shape == (256, 319)
+    assert sd['model_fine.linear_d.weight'].shape == (128, 283)
+
+
+def test_shard_range_partitions():
+    from nerf_pytorch_paeng_b200.distributed import shard_range
+    for n in (0, 1, 7, 640000, 762048):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_ray_batch_cursor():
+    from nerf_pytorch_paeng_b200.utils import GetterRayBatchIdx
+    table = torch.arange(10 * 9, dtype=torch.float32).reshape(10, 3, 3)
+    g = GetterRayBatchIdx(table)
+    i, t, e = g(4)
+    assert (i, e) == (4, 0) and torch.equal(t, table)
+    i, t, e = g(4)
+    assert (i, e) == (8, 0)
+    i, t, e = g(4)               # 12 >= 10 -> reshuffle (utils.py:54-58)
+    assert (i, e) == (4, 1) and sorted(t[:, 0, 0].tolist()) == sorted(table[:, 0, 0].tolist())
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    from nerf_pytorch_paeng_b200 import distributed
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    ctx = distributed.DistContext()
+
+    class Net:
+        def __init__(self, v):
+            self.g = torch.full((11,), float(v))
+
+        def bind_flat_grad(self):
+            return self.g
+
+    class Model:
+        pass
+    m = Model()
+    m.model_coarse, m.model_fine = Net(rank + 1), Net(10 * (rank + 1))
+    ctx.allreduce_grads(m)                               # sum over ranks
+    n = 13
+    lo, hi = ctx.shard_range(n)
+    local = torch.arange(lo, hi, dtype=torch.float32)[:, None].repeat(1, 3)
+    full = ctx.gather_rows(local, n)
+    t = ctx.allreduce_(torch.tensor([float(rank)]))
+    torch.save({'gc': m.model_coarse.g, 'gf': m.model_fine.g, 'full': full, 't': t}, os.path.join(tmp, f'r{rank}.pt'))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo(tmp_path):
+    """The multi-GPU host logic on CPU: gradient all-reduce (sum), ragged row all-gather, rank bands."""
+    world, port = 2, 29000 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        d = torch.load(os.path.join(tmp_path, f'r{r}.pt'))
+        assert torch.equal(d['gc'], torch.full((11,), 3.0)) and torch.equal(d['gf'], torch.full((11,), 30.0))
+        assert torch.equal(d['full'], torch.arange(13, dtype=torch.float32)[:, None].repeat(1, 3))
+        assert float(d['t']) == 1.0
