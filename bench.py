@@ -296,6 +296,28 @@ def run_ours(args):
            'api': 'nerf_pytorch_paeng_b200.train.train (per-image path, train.py:35-45: pinned host image -> H2D every step, '
                   'pixel selection + ray-gen + target gather + fused step + Adam on device, loss D2H)'}
 
+    # ---- second half of BASELINE.json's metric: full 800x800 coarse+fine frames/s, pixel bands sharded over ranks
+    render = None
+    if not args.no_render:
+        pose = poses_dev[0, :3, :4]
+        for _ in range(2):
+            trainer.render_frame(model, H, W, K, pose, opts, dist_ctx=dctx)
+        barrier()
+        n_fr = 3
+        t0 = time.perf_counter()
+        for i in range(n_fr):
+            rgb, disp = trainer.render_frame(model, H, W, K, poses_dev[i % len(poses), :3, :4], opts, dist_ctx=dctx)
+            frame8 = (rgb.clamp(0, 1) * 255).to(torch.uint8).cpu()          # D2H of the finished frame
+        barrier()
+        fr_ms = (time.perf_counter() - t0) * 1e3 / n_fr
+        t = torch.tensor([fr_ms], device=dev)
+        if dctx:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        fr_ms = float(t)
+        fl = FLOP_PER_POINT_FWD * H * W * POINTS_PER_RAY
+        render = {'frames_per_s': 1e3 / fr_ms, 'ms_per_frame': fr_ms, 'rays_per_s': H * W / (fr_ms / 1e3), 'frame': '800x800 coarse+fine, 64+128',
+                  'achieved_tflops': fl / (fr_ms / 1e3) / 1e12 / 1.0, 'frac_of_peak_all_gpus': fl / (fr_ms / 1e3) / 1e12 / (peak_tf * world),
+                  'includes': 'ray-gen, sampling, MLP x2, compositing, band all-gather, uint8 frame D2H'}
     if rank != 0:
         return
     # ---- cpu baseline on this box's host cores (bounded sample)
@@ -312,7 +334,7 @@ def run_ours(args):
                        'precision': args.precision, 'parallelism': f'ray-sharded data parallel x{world}, NCCL all-reduce of 2x595,844 fp32 grads',
                        'l2': 'per-step working set (activation stash >= 5 GB) exceeds the 126 MB L2; ring of 8 distinct ray batches',
                        'loss': float(loss.sum())},
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'render': render, 'gpu_launches': int(launches), 'clocks': clocks,
             'gpu_launches_per_step': launches / args.steps}
     print(json.dumps(line), flush=True)
 
@@ -326,6 +348,7 @@ def main():
     ap.add_argument('--precision', type=str, default=os.environ.get('NB_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
     ap.add_argument('--cpu-rays', dest='cpu_rays', type=int, default=256)
     ap.add_argument('--no-cpu', dest='no_cpu', action='store_true')
+    ap.add_argument('--no-render', dest='no_render', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':

@@ -113,7 +113,9 @@ def render_frame(model, H, W, K, pose, opts, dist_ctx=None, chunk=None):
     eng = get_engine(pose.device)
     n = H * W
     lo, hi = (0, n) if dist_ctx is None else dist_ctx.shard_range(n)
-    chunk = chunk or opts.chunk_rays
+    # chunk_rays is a memory knob of the reference (nerf_process.py:236); the fused kernels hold no [n_pts,90]
+    # tensor, so frames are rendered in larger chunks unless the caller pins `chunk`
+    chunk = chunk or max(int(opts.chunk_rays), 65536)
     rgb = eng.empty(hi - lo, 3)
     disp = eng.empty(hi - lo)
     ndc = opts.data_type == 'llff'

@@ -424,3 +424,28 @@ def test_render_fp32_w256_vs_oracle(eng):
     # almost every ray stays within 1e-4, isolated rays may move by ~1e-3
     err = np.abs(npy(out['rgb_f']) - exp['rgb_f']).max(-1)
     assert np.quantile(err, 0.99) <= 1e-4 and err.max() <= 3e-3, (np.quantile(err, 0.99), err.max())
+
+
+def test_render_frame_matches_batchify(eng):
+    """trainer.render_frame (device ray-gen per chunk, fused path) == make_o_d -> batchify (autograd path) when both
+    consume the same Philox counter stream; also the llff/NDC variant."""
+    from nerf_pytorch_paeng_b200 import nerf_process, rays, trainer
+    from nerf_pytorch_paeng_b200.model import NeRF, get_positional_encoder
+    g = load_golden('raygen.npz')
+    torch.manual_seed(0)
+    net = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).cuda()
+    posenc = [get_positional_encoder(10)[0], get_positional_encoder(4)[0]]
+    H, W = 40, 52
+    K = np.array([[70., 0, W / 2], [0, 70., H / 2], [0, 0, 1.]])
+    pose = cu(g['pose'])
+    for data_type, near, far in (('blender', 2., 6.), ('llff', 0., 1.)):
+        opts = make_opts(data_type=data_type, near=near, far=far, chunk_rays=512, seed=5)
+        nerf_process._counter[0] = 0
+        rgb, disp = trainer.render_frame(net, H, W, K, pose, opts, chunk=512)
+        nerf_process._counter[0] = 0
+        with torch.no_grad():
+            o, d = rays.make_o_d(W, H, K, pose)
+            _, _, rgb2, disp2 = nerf_process.batchify_rays_and_render_by_chunk(o, d, net, posenc, H, W, K, opts)
+        assert rgb.shape == (H * W, 3) and disp.shape == (H * W,)
+        assert torch.equal(rgb, rgb2) and torch.equal(disp, disp2), data_type
+        assert float(rgb.min()) >= 0. and np.isfinite(npy(rgb)).all()
