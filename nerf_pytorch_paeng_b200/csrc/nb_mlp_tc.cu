@@ -54,11 +54,12 @@ constexpr uint32_t kOffAct = 0;                              // [2][4][16 KB]
 constexpr uint32_t kOffAux = 2 * kActBytes;                  // [2][16 KB]
 constexpr uint32_t kOffW = kOffAux + 2 * kBlobBytes;         // [2][32 KB]
 constexpr uint32_t kOffBar = kOffW + 2 * 32768;              // barriers (256 B)
-constexpr uint32_t kOffWc = kOffBar + 256;                   // rgb head weights [3][128] fp32 (1536 B)
-constexpr uint32_t kSmemBytes = kOffWc + 1536 + 1024;        // + alignment slack  (= 232,192 <= 232,448)
+constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;        // + alignment slack
 
 constexpr int kThreads = 320;
-constexpr int kBarEpi0 = 1;   // named barrier ids of the two epilogue groups
+constexpr int kBarEpi0 = 1;
+
+__constant__ TcSmall c_fw;   // small fp32 parameters of the network being run (see nb_mlp_tc.h)   // named barrier ids of the two epilogue groups
 
 struct FwdParams {
   const float* rays;      // [N,6]
@@ -75,6 +76,8 @@ struct FwdParams {
   TcStash st;
   float* dbg;             // optional [P,256] accumulator dump of step dbg_step
   int dbg_step;
+  long long* prof;        // optional per-CTA cycle counters [grid][8] (NB_TC_PROF diagnostic)
+  int share_w;            // 1: each weight K-block is loaded once and used by both slots (k-interleaved), 0: ping-pong
   int abl;                // ablation bits for profiling experiments (NB_TC_ABLATE env): 1 no masks, 2 no stash stores
 };
 
@@ -130,7 +133,67 @@ __device__ __forceinline__ void emb_row_to_smem(uint32_t row_addr, uint32_t r, c
   }
 }
 
-template <bool TRAIN>
+// One layer's epilogue over `nchunks` groups of 32 accumulator columns (thread = one point / TMEM lane).
+// KIND 0: bias+ReLU -> bf16 A tile | 1: same + sigma head (step 7) | 2: view layer + rgb head (step 9; A tile only
+// written in training, for the stash) | 3: feature layer, no activation (step 8).
+template <bool TRAIN, bool DBG, int KIND>
+__device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int nchunks, uint32_t t_addr, uint32_t act_base, uint32_t r,
+                                           long long pt, bool valid, uint32_t* mdst, float& sigma, float (&rgb)[3]) {
+  const float* bias = c_fw.bias[s];
+#pragma unroll 1
+  for (int c32 = 0; c32 < nchunks; ++c32) {
+    float v[32];
+    tmem_ld32(t_addr + (uint32_t)c32 * 32u, v);
+    tmem_ld_wait();
+    if (DBG) {
+      if (p.dbg != nullptr && s == p.dbg_step && valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) p.dbg[pt * 256 + c32 * 32 + j] = v[j];
+      }
+    }
+    const float* bc = bias + c32 * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += bc[j];
+    if (TRAIN && KIND != 3) {   // ReLU mask of this layer's output for the backward chain (bit j = column c32*32+j > 0)
+      uint32_t m = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) m |= (v[j] > 0.f) ? (1u << j) : 0u;
+      mdst[c32] = m;
+    }
+    if (KIND == 1) {            // sigma head on the fp32 post-ReLU trunk output (NeRF.py:43)
+      const float* w = c_fw.ws + c32 * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sigma = fmaf(fmaxf(v[j], 0.f), w[j], sigma);
+    }
+    if (KIND == 2) {            // rgb head on the fp32 post-ReLU view features (NeRF.py:50)
+      const float* w = c_fw.wc + c32 * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float hj = fmaxf(v[j], 0.f);
+        rgb[0] = fmaf(hj, w[j], rgb[0]); rgb[1] = fmaf(hj, w[128 + j], rgb[1]); rgb[2] = fmaf(hj, w[256 + j], rgb[2]);
+      }
+    }
+    if (KIND != 2 || TRAIN) {
+      // next layer's A operand (bf16, swizzled K-major): columns c32*32.. -> K-block c32/2, chunks (c32&1)*4..+3
+      const uint32_t row_addr = act_base + (uint32_t)(c32 >> 1) * kBlobBytes + r * 128u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t c = (uint32_t)((c32 & 1) * 4 + j);
+        uint32_t w0, w1, w2, w3;
+        if (KIND == 3) {        // feature layer: no activation (NeRF.py:44)
+          w0 = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]); w1 = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
+          w2 = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]); w3 = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+        } else {
+          w0 = pack_bf16_relu(v[j * 8 + 0], v[j * 8 + 1]); w1 = pack_bf16_relu(v[j * 8 + 2], v[j * 8 + 3]);
+          w2 = pack_bf16_relu(v[j * 8 + 4], v[j * 8 + 5]); w3 = pack_bf16_relu(v[j * 8 + 6], v[j * 8 + 7]);
+        }
+        st_shared_v4(row_addr + ((c ^ (r & 7u)) << 4), w0, w1, w2, w3);
+      }
+    }
+  }
+}
+
+template <bool TRAIN, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_fwd_chain_kernel(const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -156,9 +219,6 @@ mlp_fwd_chain_kernel(const FwdParams p) {
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
-  // rgb head weights: their offset in the flat buffer is not 16-byte aligned, so stage them in shared memory
-  float* s_wc = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + kOffWc);
-  for (int i = threadIdx.x; i < 384; i += kThreads) s_wc[i] = p.prm[p.L.wc + i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -167,57 +227,100 @@ mlp_fwd_chain_kernel(const FwdParams p) {
 
   if (warp == 0) {
     // ============================== weight producer ==============================
+    // every weight K-block is loaded ONCE per iteration and consumed by both slots back to back (halves the
+    // L2->SM weight stream per tile); a stage is filled by 4 concurrent bulk copies
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      long long prof_acc[1] = {0};
       for (long long it = 0; it < max_it; ++it) {
+        if (tile_of(0, it) >= n_tiles) break;
 #pragma unroll 1
         for (int s = 0; s < kFwdSteps; ++s) {
           const uint32_t bytes = fwd_blob_bytes(s);
           const uint8_t* src = p.wpk + fwd_w_off(s);
-          for (int slot = 0; slot < 2; ++slot) {
-            if (tile_of(slot, it) >= n_tiles) continue;
+          const int reps = (p.share_w || tile_of(1, it) >= n_tiles) ? 1 : 2;
+          for (int rep = 0; rep < reps; ++rep)
             for (int kb = 0; kb < fwd_nkb(s); ++kb) {
-              mbar_wait(b_wempty + 8 * stage, phase ^ 1);
+              { const long long t0 = clock64(); mbar_wait(b_wempty + 8 * stage, phase ^ 1); prof_acc[0] += clock64() - t0; }
               mbar_expect_tx(b_wfull + 8 * stage, bytes);
-              bulk_g2s(s_w + stage * 32768u, src + (size_t)kb * bytes, bytes, b_wfull + 8 * stage);
+              const uint32_t q4 = bytes >> 2;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                bulk_g2s(s_w + stage * 32768u + i * q4, src + (size_t)kb * bytes + i * q4, q4, b_wfull + 8 * stage);
               stage ^= 1; if (stage == 0) phase ^= 1;
             }
-          }
         }
       }
+      (void)prof_acc;
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     uint32_t stage = 0, phase = 0, par_a[2] = {0, 0};
+    long long pa = 0, pw = 0;
+    const long long tstart = clock64();
     for (long long it = 0; it < max_it; ++it) {
+      const bool v0 = tile_of(0, it) < n_tiles, v1 = tile_of(1, it) < n_tiles;
+      if (!v0) break;
 #pragma unroll 1
       for (int s = 0; s < kFwdSteps; ++s) {
         const uint32_t idesc = umma_idesc(128, fwd_n(s), 0, 0);
-        for (int slot = 0; slot < 2; ++slot) {
-          if (tile_of(slot, it) >= n_tiles) continue;
-          mbar_wait(b_aready + 8 * slot, par_a[slot]); par_a[slot] ^= 1;
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
-          for (int kb = 0; kb < fwd_nkb(s); ++kb) {
-            mbar_wait(b_wfull + 8 * stage, phase);
+        const int nkb = fwd_nkb(s);
+        if (!p.share_w) {
+          // ping-pong: slot 0's whole step, then slot 1's (its epilogue overlaps the other slot's MMAs)
+          for (int slot = 0; slot < 2; ++slot) {
+            if (slot == 1 && !v1) break;
+            { const long long t0 = clock64(); mbar_wait(b_aready + 8 * slot, par_a[slot]); pa += clock64() - t0; }
+            par_a[slot] ^= 1;
             tc_fence_after();
-            if (lane == 0) {
-              const int src = fwd_a_src(s, kb);
+            const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
+            for (int kb = 0; kb < nkb; ++kb) {
+              { const long long t0 = clock64(); mbar_wait(b_wfull + 8 * stage, phase); pw += clock64() - t0; }
+              tc_fence_after();
+              if (lane == 0) {
+                const int src = fwd_a_src(s, kb);
+                const uint32_t a_addr = (src < 0) ? (s_aux + slot * kBlobBytes) : (s_act + slot * kActBytes + (uint32_t)src * kBlobBytes);
+                const uint32_t b_addr = s_w + stage * 32768u;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                  umma_ss(d_tmem, umma_desc(a_addr + k4 * 32u, 16, 1024), umma_desc(b_addr + k4 * 32u, 16, 1024), idesc,
+                          (kb | k4) ? 1u : 0u);
+                umma_commit(b_wempty + 8 * stage);
+                if (kb == nkb - 1) umma_commit(b_accready + 8 * slot);
+              }
+              __syncwarp();
+              stage ^= 1; if (stage == 0) phase ^= 1;
+            }
+          }
+          continue;
+        }
+        mbar_wait(b_aready + 0, par_a[0]); par_a[0] ^= 1;
+        if (v1) { mbar_wait(b_aready + 8, par_a[1]); par_a[1] ^= 1; }
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(b_wfull + 8 * stage, phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const int src = fwd_a_src(s, kb);
+            const uint32_t b_addr = s_w + stage * 32768u;
+#pragma unroll
+            for (int slot = 0; slot < 2; ++slot) {
+              if (slot == 1 && !v1) break;
               const uint32_t a_addr = (src < 0) ? (s_aux + slot * kBlobBytes) : (s_act + slot * kActBytes + (uint32_t)src * kBlobBytes);
-              const uint32_t b_addr = s_w + stage * 32768u;
+              const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4)
                 umma_ss(d_tmem, umma_desc(a_addr + k4 * 32u, 16, 1024), umma_desc(b_addr + k4 * 32u, 16, 1024), idesc,
                         (kb | k4) ? 1u : 0u);
-              umma_commit(b_wempty + 8 * stage);                          // stage is free once these MMAs retire
-              if (kb == fwd_nkb(s) - 1) umma_commit(b_accready + 8 * slot);  // accumulator complete
+              if (kb == nkb - 1) umma_commit(b_accready + 8 * slot);   // this slot's accumulator is complete
             }
-            __syncwarp();
-            stage ^= 1; if (stage == 0) phase ^= 1;
+            umma_commit(b_wempty + 8 * stage);                         // stage is free once both slots' MMAs retire
           }
+          __syncwarp();
+          stage ^= 1; if (stage == 0) phase ^= 1;
         }
       }
     }
+    if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 1] = pa; p.prof[blockIdx.x * 8 + 2] = pw; p.prof[blockIdx.x * 8 + 3] = clock64() - tstart; }
   } else {
     // ============================== epilogue groups ==============================
     const int slot = (warp - 2) >> 2;
@@ -229,8 +332,7 @@ mlp_fwd_chain_kernel(const FwdParams p) {
     const int bar_id = kBarEpi0 + slot;
     uint32_t par_acc = 0;
     bool store_pending = false;                              // a bulk store issued by grp_tid 0 still reads smem
-    const float* prm = p.prm;
-
+    long long pe_wait = 0, pe_body = 0, pe_pro = 0;
     for (long long it = 0; it < max_it; ++it) {
       const long long tile = tile_of(slot, it);
       if (tile >= n_tiles) break;
@@ -261,81 +363,25 @@ mlp_fwd_chain_kernel(const FwdParams p) {
       mbar_arrive(b_aready + 8 * slot);
 
       float sigma = 0.f;
+      float rgb[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int s = 0; s < kFwdSteps; ++s) {
+        long long t_e0 = clock64();
         mbar_wait(b_accready + 8 * slot, par_acc); par_acc ^= 1;
         tc_fence_after();
+        { const long long t1 = clock64(); pe_wait += t1 - t_e0; t_e0 = t1; }
         if (TRAIN && store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, 128); store_pending = false; }
-        const int ncols = fwd_n(s);
-        const float* bias = prm + (s < 8 ? p.L.b[s] : (s == 8 ? p.L.bf : p.L.bd));
-        float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-        uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int c32 = 0; c32 < 8; ++c32) {
-          if (c32 * 32 >= ncols) break;
-          float v[32];
-          tmem_ld32(t_addr + (uint32_t)c32 * 32u, v);
-          tmem_ld_wait();
-          if (p.dbg != nullptr && s == p.dbg_step && valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) p.dbg[pt * 256 + c32 * 32 + j] = v[j];
-          }
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c32 * 32) + j4);
-            v[j4 * 4 + 0] += b4.x; v[j4 * 4 + 1] += b4.y; v[j4 * 4 + 2] += b4.z; v[j4 * 4 + 3] += b4.w;
-          }
-          if (TRAIN && s != 8 && !(p.abl & 1)) {   // ReLU mask of this layer's output for the backward chain (bit j = column c32*32+j > 0)
-            uint32_t m = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) m |= (v[j] > 0.f) ? (1u << j) : 0u;
-            mw[c32] = m;
-          }
-          if (s == 7) {           // sigma head on the fp32 post-ReLU trunk output (NeRF.py:43)
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(prm + p.L.ws + c32 * 32) + j4);
-              sigma = fmaf(fmaxf(v[j4 * 4 + 0], 0.f), w4.x, sigma); sigma = fmaf(fmaxf(v[j4 * 4 + 1], 0.f), w4.y, sigma);
-              sigma = fmaf(fmaxf(v[j4 * 4 + 2], 0.f), w4.z, sigma); sigma = fmaf(fmaxf(v[j4 * 4 + 3], 0.f), w4.w, sigma);
-            }
-          }
-          if (s == 9) {           // rgb head on the fp32 post-ReLU view features (NeRF.py:50)
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 a4 = reinterpret_cast<const float4*>(s_wc + 0 * 128 + c32 * 32)[j4];
-              const float4 g4 = reinterpret_cast<const float4*>(s_wc + 1 * 128 + c32 * 32)[j4];
-              const float4 c4 = reinterpret_cast<const float4*>(s_wc + 2 * 128 + c32 * 32)[j4];
-              const float h0 = fmaxf(v[j4 * 4 + 0], 0.f), h1 = fmaxf(v[j4 * 4 + 1], 0.f), h2 = fmaxf(v[j4 * 4 + 2], 0.f),
-                          h3 = fmaxf(v[j4 * 4 + 3], 0.f);
-              rgb0 = fmaf(h0, a4.x, rgb0); rgb0 = fmaf(h1, a4.y, rgb0); rgb0 = fmaf(h2, a4.z, rgb0); rgb0 = fmaf(h3, a4.w, rgb0);
-              rgb1 = fmaf(h0, g4.x, rgb1); rgb1 = fmaf(h1, g4.y, rgb1); rgb1 = fmaf(h2, g4.z, rgb1); rgb1 = fmaf(h3, g4.w, rgb1);
-              rgb2 = fmaf(h0, c4.x, rgb2); rgb2 = fmaf(h1, c4.y, rgb2); rgb2 = fmaf(h2, c4.z, rgb2); rgb2 = fmaf(h3, c4.w, rgb2);
-            }
-          }
-          // next layer's A operand (bf16, swizzled K-major): columns c32*32.. -> K-block c32/2, chunks (c32&1)*4..+3
-          if (s != 9 || TRAIN) {
-            const uint32_t row_addr = act_base + (uint32_t)(c32 >> 1) * kBlobBytes + r * 128u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t c = (uint32_t)((c32 & 1) * 4 + j);
-              uint32_t w0, w1, w2, w3;
-              if (s == 8) {   // feature layer: no activation (NeRF.py:44)
-                w0 = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]); w1 = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
-                w2 = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]); w3 = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
-              } else {
-                w0 = pack_bf16_relu(v[j * 8 + 0], v[j * 8 + 1]); w1 = pack_bf16_relu(v[j * 8 + 2], v[j * 8 + 3]);
-                w2 = pack_bf16_relu(v[j * 8 + 4], v[j * 8 + 5]); w3 = pack_bf16_relu(v[j * 8 + 6], v[j * 8 + 7]);
-              }
-              st_shared_v4(row_addr + ((c ^ (r & 7u)) << 4), w0, w1, w2, w3);
-            }
-          }
-        }
-        if (TRAIN && s != 8) {   // 32 contiguous bytes per row: full-sector stores
-          const int layer = s < 8 ? s : 8;
-          uint4* mdst = reinterpret_cast<uint4*>(p.stash + p.st.off_mask) + (((size_t)tile * 9 + layer) * 128 + r) * 2;
-          mdst[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-          mdst[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
-        }
+        // The chunk loop is deliberately NOT unrolled and is specialised per step kind: one 32-column body is
+        // ~200 instructions (3 KB) and stays resident in the instruction cache across chunks, steps and tiles.  (A fully
+        // unrolled epilogue streamed ~30 KB of code per step through the I-cache and ran 5x slower: stall_no_inst.)
+        const int kind = (s == 7) ? 1 : (s == 9 ? 2 : (s == 8 ? 3 : 0));
+        uint32_t* mdst = nullptr;
+        if (TRAIN && s != 8)
+          mdst = reinterpret_cast<uint32_t*>(p.stash + p.st.off_mask) + (((size_t)tile * 9 + (s < 8 ? s : 8)) * 128 + r) * 8;
+        if (kind == 0) epi_chunks<TRAIN, DBG, 0>(p, s, 8, t_addr, act_base, r, pt, valid, mdst, sigma, rgb);
+        else if (kind == 1) epi_chunks<TRAIN, DBG, 1>(p, s, 8, t_addr, act_base, r, pt, valid, mdst, sigma, rgb);
+        else if (kind == 2) epi_chunks<TRAIN, DBG, 2>(p, s, 4, t_addr, act_base, r, pt, valid, mdst, sigma, rgb);
+        else epi_chunks<TRAIN, DBG, 3>(p, s, 8, t_addr, act_base, r, pt, valid, mdst, sigma, rgb);
         if (s == 5) {
           // the step-9 operand needs PE(viewdir) in aux; aux (PE of the point) was last read by MMA step 5, now retired
           if (p.x_emb == nullptr) pe_row_to_smem<4>(aux_base + r * 128u, r, dirx, diry, dirz, false);
@@ -354,15 +400,18 @@ mlp_fwd_chain_kernel(const FwdParams p) {
           }
           store_pending = true;
         }
+        pe_body += clock64() - t_e0;
         if (s < 9) {
           mbar_arrive(b_aready + 8 * slot);
         } else if (valid) {
-          const float4 bc = make_float4(prm[p.L.bc], prm[p.L.bc + 1], prm[p.L.bc + 2], prm[p.L.bs]);
-          reinterpret_cast<float4*>(p.raw)[pt] = make_float4(rgb0 + bc.x, rgb1 + bc.y, rgb2 + bc.z, sigma + bc.w);
+          const float4 bc = make_float4(c_fw.bc[0], c_fw.bc[1], c_fw.bc[2], c_fw.bc[3]);
+          reinterpret_cast<float4*>(p.raw)[pt] = make_float4(rgb[0] + bc.x, rgb[1] + bc.y, rgb[2] + bc.z, sigma + bc.w);
         }
       }
     }
     if (TRAIN && store_pending && grp_tid == 0) bulk_wait_all0();
+    if (p.prof && grp_tid == 0) { p.prof[blockIdx.x * 8 + 4 + slot * 2] = pe_wait; p.prof[blockIdx.x * 8 + 5 + slot * 2] = pe_body; }
+    (void)pe_pro;
   }
   tc_fence_before();
   __syncthreads();
@@ -385,7 +434,23 @@ constexpr int kMaxBlobs = 80;
 struct PackParams { BlobDesc b[kMaxBlobs]; int n; };
 
 __global__ void __launch_bounds__(256)
-pack_kernel(const PackParams pp, const float* __restrict__ prm, uint8_t* __restrict__ out) {
+pack_kernel(const PackParams pp, const float* __restrict__ prm, uint8_t* __restrict__ out, NbParamLayout L, uint32_t small_off) {
+  if ((int)blockIdx.y == pp.n) {       // last row of blocks: gather the small fp32 parameters (TcSmall)
+    TcSmall* sm = reinterpret_cast<TcSmall*>(out + small_off);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 10 * 256; i += gridDim.x * blockDim.x) {
+      const int s = i >> 8, c = i & 255;
+      float v = 0.f;
+      if (s < 8) v = prm[L.b[s] + c];
+      else if (s == 8) v = prm[L.bf + c];
+      else if (c < 128) v = prm[L.bd + c];
+      sm->bias[s][c] = v;
+      if (s == 0) sm->ws[c] = prm[L.ws + c];
+      if (i < 384) sm->wc[i] = prm[L.wc + i];
+      if (i < 3) sm->bc[i] = prm[L.bc + i];
+      if (i == 3) sm->bc[3] = prm[L.bs];
+    }
+    return;
+  }
   const BlobDesc d = pp.b[blockIdx.y];
   const int total = d.n_rows * 8;    // 16-byte chunks
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -421,7 +486,8 @@ bool nb_tc_supported(const nb_mlp_desc& d) {
 }
 
 size_t nb_tc_fwd_packed_bytes() { return fwd_w_off(kFwdSteps); }
-size_t nb_tc_packed_bytes(const nb_mlp_desc&) { return nb_tc_fwd_packed_bytes() + nb_tc_bwd_packed_bytes(); }
+size_t nb_tc_small_offset() { return nb_tc_fwd_packed_bytes() + nb_tc_bwd_packed_bytes(); }
+size_t nb_tc_packed_bytes(const nb_mlp_desc&) { return nb_tc_small_offset() + sizeof(TcSmall); }
 
 TcStash nb_tc_stash_layout(long long P) {
   TcStash s;
@@ -461,24 +527,44 @@ int nb_tc_pack(nb_handle_t h, const nb_mlp_desc* d, const float* params, void* p
     add_blob(pp, off, src, ld, tr, n0, k0, rows, n_lim, k_lim);
   });
   if (pp.n > kMaxBlobs) { NB_SET_ERR(h, "nb_tc_pack: too many blobs"); return NB_ERR_INVALID; }
-  dim3 grid(4, pp.n);
-  pack_kernel<<<grid, 256, 0, st>>>(pp, params, (uint8_t*)packed);
+  dim3 grid(4, pp.n + 1);
+  pack_kernel<<<grid, 256, 0, st>>>(pp, params, (uint8_t*)packed, L, (uint32_t)nb_tc_small_offset());
   NB_LAUNCHED(h);
   return NB_OK;
 }
 
 static int launch_fwd(nb_handle_t h, FwdParams& fp, bool train, cudaStream_t st) {
-  static bool attr_done[2] = {false, false};
-  auto kern = train ? mlp_fwd_chain_kernel<true> : mlp_fwd_chain_kernel<false>;
-  if (!attr_done[train]) {
+  static bool attr_done[3] = {false, false, false};
+  const bool dbg = fp.dbg != nullptr;
+  auto kern = dbg ? mlp_fwd_chain_kernel<false, true> : (train ? mlp_fwd_chain_kernel<true, false> : mlp_fwd_chain_kernel<false, false>);
+  const int ki = dbg ? 2 : (train ? 1 : 0);
+  if (!attr_done[ki]) {
     NB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_done[train] = true;
+    attr_done[ki] = true;
   }
+  NB_CUDA(h, cudaMemcpyToSymbolAsync(c_fw, fp.wpk + nb_tc_small_offset(), sizeof(TcSmall), 0, cudaMemcpyDeviceToDevice, st));
   const long long n_tiles = (fp.P + 127) / 128;
   long long grid = (n_tiles + 1) / 2;
   if (grid > h->sm_count) grid = h->sm_count;
+  static long long* prof_dev = nullptr;
+  const bool prof = getenv("NB_TC_PROF") != nullptr;
+  if (prof) {
+    if (!prof_dev) cudaMalloc(&prof_dev, 256 * 8 * sizeof(long long));
+    cudaMemsetAsync(prof_dev, 0, 256 * 8 * sizeof(long long), st);
+    fp.prof = prof_dev;
+  }
   kern<<<(int)grid, kThreads, kSmemBytes, st>>>(fp);
   NB_LAUNCHED(h);
+  if (prof) {   // diagnostic only: synchronous read-back of the per-CTA cycle counters
+    static long long host[256 * 8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, prof_dev, sizeof(host), cudaMemcpyDeviceToHost);
+    double a[8] = {0};
+    for (int b = 0; b < grid; ++b) for (int k = 0; k < 8; ++k) a[k] += (double)host[b * 8 + k] / grid;
+    fprintf(stderr, "nb_tc prof (avg cycles/CTA, P=%lld train=%d): epi1_tmem_ld=%.0f mma_wait_aready=%.0f mma_wait_wfull=%.0f "
+            "mma_total=%.0f epi0_wait=%.0f epi0_body=%.0f epi1_wait=%.0f epi1_body=%.0f\n", fp.P, (int)train, a[0], a[1], a[2], a[3],
+            a[4], a[5], a[6], a[7]);
+  }
   return NB_OK;
 }
 
@@ -493,6 +579,7 @@ int nb_tc_forward(nb_handle_t h, const nb_mlp_desc* d, const float* params, cons
   fp.stash = (uint8_t*)act_save; fp.st = nb_tc_stash_layout(P);
   fp.dbg = nullptr; fp.dbg_step = -1;
   { const char* e = getenv("NB_TC_ABLATE"); fp.abl = e ? atoi(e) : 0; }
+  { const char* e = getenv("NB_TC_SHARE_W"); fp.share_w = e ? atoi(e) : 0; }
   return launch_fwd(h, fp, act_save != nullptr, st);
 }
 

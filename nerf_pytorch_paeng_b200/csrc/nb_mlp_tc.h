@@ -20,6 +20,18 @@ struct TcStash {
 };
 TcStash nb_tc_stash_layout(long long P);
 
+// Small fp32 parameters every epilogue thread needs for every column (biases, sigma / rgb head weights).  With
+// 227 KB of shared memory per CTA the L1 is empty, so reading them through the global path costs an L2 round
+// trip per chunk; they are gathered once per weight update (nb_mlp_pack) behind the packed blobs and copied to
+// __constant__ memory before each launch, where warp-uniform reads are broadcast from the constant cache.
+struct TcSmall {
+  float bias[10][256];   // forward chain steps 0..9: b0..b7, b_feat, b_d (128 used)
+  float ws[256];         // linear_density.weight
+  float wc[384];         // linear_color.weight [3][128]
+  float bc[4];           // linear_color.bias[0..2], linear_density.bias
+};
+size_t nb_tc_small_offset();   // byte offset of the TcSmall block inside the packed buffer
+
 size_t nb_tc_fwd_packed_bytes();
 size_t nb_tc_bwd_packed_bytes();
 size_t nb_tc_bwd_ws_bytes(const nb_mlp_desc& d, long long P);

@@ -57,9 +57,10 @@ constexpr uint32_t kOffAct = 0;
 constexpr uint32_t kOffAux = 2 * kActBytes;
 constexpr uint32_t kOffW = kOffAux + 2 * kBlobBytes;
 constexpr uint32_t kOffBar = kOffW + 2 * 32768;
-constexpr uint32_t kOffWc = kOffBar + 256;
-constexpr uint32_t kSmemBytes = kOffWc + 1536 + 1024;
+constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;
 constexpr int kThreads = 320;
+
+__constant__ TcSmall c_bw;   // small fp32 parameters (sigma / rgb head weights) of the network being differentiated
 
 struct DgradParams {
   long long P;
@@ -95,8 +96,6 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
-  float* s_wc = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + kOffWc);
-  for (int i = threadIdx.x; i < 384; i += kThreads) s_wc[i] = p.prm[p.L.wc + i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -104,20 +103,21 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
 
   if (warp == 0) {
+    // weight producer: every W^T K-block once per iteration, shared by both slots; 4 concurrent bulk copies per stage
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (long long it = 0; it < max_it; ++it) {
+        if (tile_of(0, it) >= n_tiles) break;
 #pragma unroll 1
         for (int b = 0; b < kBwdSteps; ++b) {
           const uint8_t* src = p.wpk + bwd_w_off(b);
-          for (int slot = 0; slot < 2; ++slot) {
-            if (tile_of(slot, it) >= n_tiles) continue;
-            for (int kb = 0; kb < bwd_nkb(b); ++kb) {
-              mbar_wait(b_wempty + 8 * stage, phase ^ 1);
-              mbar_expect_tx(b_wfull + 8 * stage, 32768u);
-              bulk_g2s(s_w + stage * 32768u, src + (size_t)kb * 32768u, 32768u, b_wfull + 8 * stage);
-              stage ^= 1; if (stage == 0) phase ^= 1;
-            }
+          for (int kb = 0; kb < bwd_nkb(b); ++kb) {
+            mbar_wait(b_wempty + 8 * stage, phase ^ 1);
+            mbar_expect_tx(b_wfull + 8 * stage, 32768u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              bulk_g2s(s_w + stage * 32768u + i * 8192u, src + (size_t)kb * 32768u + i * 8192u, 8192u, b_wfull + 8 * stage);
+            stage ^= 1; if (stage == 0) phase ^= 1;
           }
         }
       }
@@ -126,29 +126,34 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
     uint32_t stage = 0, phase = 0, par_a[2] = {0, 0};
     const uint32_t idesc = umma_idesc(128, 256, 0, 0);
     for (long long it = 0; it < max_it; ++it) {
+      const bool v0 = tile_of(0, it) < n_tiles, v1 = tile_of(1, it) < n_tiles;
+      if (!v0) break;
 #pragma unroll 1
       for (int b = 0; b < kBwdSteps; ++b) {
-        for (int slot = 0; slot < 2; ++slot) {
-          if (tile_of(slot, it) >= n_tiles) continue;
-          mbar_wait(b_aready + 8 * slot, par_a[slot]); par_a[slot] ^= 1;
+        mbar_wait(b_aready + 0, par_a[0]); par_a[0] ^= 1;
+        if (v1) { mbar_wait(b_aready + 8, par_a[1]); par_a[1] ^= 1; }
+        tc_fence_after();
+        const int nkb = bwd_nkb(b);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(b_wfull + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
-          for (int kb = 0; kb < bwd_nkb(b); ++kb) {
-            mbar_wait(b_wfull + 8 * stage, phase);
-            tc_fence_after();
-            if (lane == 0) {
+          if (lane == 0) {
+            const uint32_t b_addr = s_w + stage * 32768u;
+#pragma unroll
+            for (int slot = 0; slot < 2; ++slot) {
+              if (slot == 1 && !v1) break;
               const uint32_t a_addr = s_act + slot * kActBytes + (uint32_t)kb * kBlobBytes;
-              const uint32_t b_addr = s_w + stage * 32768u;
+              const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4)
                 umma_ss(d_tmem, umma_desc(a_addr + k4 * 32u, 16, 1024), umma_desc(b_addr + k4 * 32u, 16, 1024), idesc,
                         (kb | k4) ? 1u : 0u);
-              umma_commit(b_wempty + 8 * stage);
-              if (kb == bwd_nkb(b) - 1) umma_commit(b_accready + 8 * slot);
+              if (kb == nkb - 1) umma_commit(b_accready + 8 * slot);
             }
-            __syncwarp();
-            stage ^= 1; if (stage == 0) phase ^= 1;
+            umma_commit(b_wempty + 8 * stage);
           }
+          __syncwarp();
+          stage ^= 1; if (stage == 0) phase ^= 1;
         }
       }
     }
@@ -162,8 +167,6 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
     const int bar_id = 1 + slot;
     uint32_t par_acc = 0;
     bool store_pending = false;
-    const float* prm = p.prm;
-
     for (long long it = 0; it < max_it; ++it) {
       const long long tile = tile_of(slot, it);
       if (tile >= n_tiles) break;
@@ -176,14 +179,15 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
       const uint4 gm = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)8 * 128 * 8));       // mask of g (128 columns)
       const uint32_t gmw[4] = {gm.x, gm.y, gm.z, gm.w};
       if (store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, 128); store_pending = false; }
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 16; ++c) {
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int col = c * 8 + j;
-          const float val = fmaf(dr.x, s_wc[col], fmaf(dr.y, s_wc[128 + col], dr.z * s_wc[256 + col]));
-          v[j] = ((gmw[col >> 5] >> (col & 31)) & 1u) ? val : 0.f;
+          const float val = fmaf(dr.x, c_bw.wc[col], fmaf(dr.y, c_bw.wc[128 + col], dr.z * c_bw.wc[256 + col]));
+          const uint32_t gmsel = (c & 8) ? ((c & 4) ? gmw[3] : gmw[2]) : ((c & 4) ? gmw[1] : gmw[0]);
+          v[j] = ((gmsel >> (col & 31)) & 1u) ? val : 0.f;
         }
         st_shared_v4(act_base + (uint32_t)(c >> 3) * kBlobBytes + sw128_chunk(r, (uint32_t)(c & 7)), pack_bf16(v[0], v[1]),
                      pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -217,21 +221,22 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
         mbar_wait(b_accready + 8 * slot, par_acc); par_acc ^= 1;
         tc_fence_after();
         if (store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, 128); store_pending = false; }
-#pragma unroll
+        // rolled on purpose: one 32-column body stays resident in the instruction cache (see nb_mlp_tc.cu)
+#pragma unroll 1
         for (int c32 = 0; c32 < 8; ++c32) {
           float v[32];
           tmem_ld32(t_addr + (uint32_t)c32 * 32u, v);
           tmem_ld_wait();
           if (b == 1) {   // density head: d h7 += d sigma * W_sigma   (NeRF.py:43)
+            const float* w = c_bw.ws + c32 * 32;
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(prm + p.L.ws + c32 * 32) + j4);
-              v[j4 * 4 + 0] = fmaf(dr.w, w4.x, v[j4 * 4 + 0]); v[j4 * 4 + 1] = fmaf(dr.w, w4.y, v[j4 * 4 + 1]);
-              v[j4 * 4 + 2] = fmaf(dr.w, w4.z, v[j4 * 4 + 2]); v[j4 * 4 + 3] = fmaf(dr.w, w4.w, v[j4 * 4 + 3]);
-            }
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(dr.w, w[j], v[j]);
           }
           {
-            const uint32_t m = mq[c32];
+            const uint32_t m01 = (c32 & 1) ? mq[1] : mq[0], m23 = (c32 & 1) ? mq[3] : mq[2];
+            const uint32_t m45 = (c32 & 1) ? mq[5] : mq[4], m67 = (c32 & 1) ? mq[7] : mq[6];
+            const uint32_t m03 = (c32 & 2) ? m23 : m01, m47 = (c32 & 2) ? m67 : m45;
+            const uint32_t m = (c32 & 4) ? m47 : m03;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (!((m >> j) & 1u)) v[j] = 0.f;
@@ -459,6 +464,8 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
     memset(&dp, 0, sizeof(dp));
     dp.P = P; dp.wpk = (const uint8_t*)packed + nb_tc_fwd_packed_bytes(); dp.prm = params; dp.L = L; dp.d_raw = d_raw;
     dp.stash = (const uint8_t*)act_save; dp.st = S; dp.ws = (uint8_t*)ws; dp.w = W;
+    NB_CUDA(h, cudaMemcpyToSymbolAsync(c_bw, (const uint8_t*)packed + nb_tc_small_offset(), sizeof(TcSmall), 0,
+                                       cudaMemcpyDeviceToDevice, st));
     long long grid = (n_tiles + 1) / 2;
     if (grid > h->sm_count) grid = h->sm_count;
     mlp_dgrad_chain_kernel<<<(int)grid, kThreads, kSmemBytes, st>>>(dp);
