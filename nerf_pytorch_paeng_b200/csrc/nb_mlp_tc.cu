@@ -77,7 +77,6 @@ struct FwdParams {
   float* dbg;             // optional [P,256] accumulator dump of step dbg_step
   int dbg_step;
   long long* prof;        // optional per-CTA cycle counters [grid][8] (NB_TC_PROF diagnostic)
-  int share_w;            // 1: each weight K-block is loaded once and used by both slots (k-interleaved), 0: ping-pong
   int abl;                // ablation bits for profiling experiments (NB_TC_ABLATE env): 1 no masks, 2 no stash stores
 };
 
@@ -154,11 +153,14 @@ __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int nchunk
     const float* bc = bias + c32 * 32;
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += bc[j];
-    if (TRAIN && KIND != 3) {   // ReLU mask of this layer's output for the backward chain (bit j = column c32*32+j > 0)
+    if (TRAIN && KIND != 3) {
+      // ReLU mask of this layer's output for the backward chain, one funnel shift per element: bit (31-j) of the
+      // word = SIGN bit of column c32*32+j, i.e. set = inactive.  (An exact +0.0 pre-activation counts as active,
+      // where torch's relu' is 0: a measure-zero difference.)
       uint32_t m = 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) m |= (v[j] > 0.f) ? (1u << j) : 0u;
-      mdst[c32] = m;
+      for (int j = 0; j < 32; ++j) m = __funnelshift_l(__float_as_uint(v[j]), m, 1);
+      if (mdst != nullptr) mdst[c32] = m;
     }
     if (KIND == 1) {            // sigma head on the fp32 post-ReLU trunk output (NeRF.py:43)
       const float* w = c_fw.ws + c32 * 32;
@@ -193,134 +195,147 @@ __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int nchunk
   }
 }
 
-template <bool TRAIN, bool DBG>
+// CTA2 = true: the kernel runs as thread-block clusters of two CTAs on one TPC and every GEMM is a
+// tcgen05.mma.cta_group::2 with M = 256: CTA 0 (leader) owns rows 0..127, CTA 1 rows 128..255, each keeps its own
+// activation tiles / TMEM accumulators, and each streams only ITS HALF of every weight blob (N/2 rows), halving the
+// L2->SM weight stream per tile and doubling the depth of the weight ring (4 x 16 KB).  Only the leader issues MMAs;
+// the peer's MMA warp forwards "my half of stage k has landed" to the leader; tcgen05.commit multicasts the
+// stage-free / accumulator-ready arrivals to both CTAs; epilogue threads of the peer arrive on the leader's
+// a_ready barrier through DSMEM (mapa + mbarrier.arrive.release.cluster).
+template <bool TRAIN, bool DBG, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_fwd_chain_kernel(const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_act = sbase + kOffAct, s_aux = sbase + kOffAux, s_w = sbase + kOffW, s_bar = sbase + kOffBar;
-  // barriers (8 bytes each): w_full[2] w_empty[2] a_ready[2] acc_ready[2] ; tmem ptr at +64
-  const uint32_t b_wfull = s_bar, b_wempty = s_bar + 16, b_aready = s_bar + 32, b_accready = s_bar + 48, s_tmem = s_bar + 64;
+  // barriers (8 bytes each): w_full[4] w_empty[4] p_full[4] a_ready[2] acc_ready[2] ; tmem ptr
+  const uint32_t b_wfull = s_bar, b_wempty = s_bar + 32, b_pfull = s_bar + 64, b_aready = s_bar + 96, b_accready = s_bar + 112,
+                 s_tmem = s_bar + 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t NSTAGE = CTA2 ? 4u : 2u;
+  constexpr uint32_t STAGE_BYTES = CTA2 ? 16384u : 32768u;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
 
   const long long n_tiles = (p.P + 127) / 128;
-  // slot s of CTA b owns tiles (2*b + s) + i * 2 * gridDim.x
-  const long long tile_stride = 2LL * gridDim.x;
-  auto tile_of = [&](int slot, long long it) { return 2LL * blockIdx.x + slot + it * tile_stride; };
-  const long long max_it = (n_tiles + tile_stride - 1) / tile_stride;
+  // work units: CTA2: "pair tiles" q (tiles 2q, 2q+1 for ranks 0,1); else single tiles
+  const long long n_units = CTA2 ? (n_tiles + 1) / 2 : n_tiles;
+  const long long ncl = CTA2 ? gridDim.x / 2 : gridDim.x, cid = CTA2 ? blockIdx.x / 2 : blockIdx.x;
+  auto unit_of = [&](int slot, long long it) { return (it * ncl + cid) * 2 + slot; };
+  const long long max_it = (n_units + 2 * ncl - 1) / (2 * ncl);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (uint32_t i = 0; i < 4; ++i) {
       mbar_init(b_wfull + 8 * i, 1);
       mbar_init(b_wempty + 8 * i, 1);
-      mbar_init(b_aready + 8 * i, 128);
+      mbar_init(b_pfull + 8 * i, 1);
+    }
+    for (uint32_t i = 0; i < 2; ++i) {
+      mbar_init(b_aready + 8 * i, CTA2 ? 256 : 128);
       mbar_init(b_accready + 8 * i, 1);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(s_tmem, 512);
+  if (warp == 1) { if (CTA2) tmem_alloc2(s_tmem, 512); else tmem_alloc(s_tmem, 512); }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();      // peer barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
 
   if (warp == 0) {
-    // ============================== weight producer ==============================
-    // every weight K-block is loaded ONCE per iteration and consumed by both slots back to back (halves the
-    // L2->SM weight stream per tile); a stage is filled by 4 concurrent bulk copies
+    // ============================== weight producer (every CTA) ==============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      long long prof_acc[1] = {0};
       for (long long it = 0; it < max_it; ++it) {
-        if (tile_of(0, it) >= n_tiles) break;
 #pragma unroll 1
         for (int s = 0; s < kFwdSteps; ++s) {
-          const uint32_t bytes = fwd_blob_bytes(s);
-          const uint8_t* src = p.wpk + fwd_w_off(s);
-          const int reps = (p.share_w || tile_of(1, it) >= n_tiles) ? 1 : 2;
-          for (int rep = 0; rep < reps; ++rep)
+          const uint32_t bytes = CTA2 ? fwd_blob_bytes(s) / 2 : fwd_blob_bytes(s);      // this CTA's share of the N rows
+          const uint8_t* src = p.wpk + fwd_w_off(s) + (CTA2 ? rank * bytes : 0u);
+          for (int slot = 0; slot < 2; ++slot) {
+            if (unit_of(slot, it) >= n_units) continue;
             for (int kb = 0; kb < fwd_nkb(s); ++kb) {
-              { const long long t0 = clock64(); mbar_wait(b_wempty + 8 * stage, phase ^ 1); prof_acc[0] += clock64() - t0; }
+              mbar_wait(b_wempty + 8 * stage, phase ^ 1);
               mbar_expect_tx(b_wfull + 8 * stage, bytes);
               const uint32_t q4 = bytes >> 2;
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                bulk_g2s(s_w + stage * 32768u + i * q4, src + (size_t)kb * bytes + i * q4, q4, b_wfull + 8 * stage);
-              stage ^= 1; if (stage == 0) phase ^= 1;
+                bulk_g2s(s_w + stage * STAGE_BYTES + i * q4, src + (size_t)kb * fwd_blob_bytes(s) + i * q4, q4, b_wfull + 8 * stage);
+              if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
+          }
         }
       }
-      (void)prof_acc;
     }
   } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
     uint32_t stage = 0, phase = 0, par_a[2] = {0, 0};
-    long long pa = 0, pw = 0;
-    const long long tstart = clock64();
-    for (long long it = 0; it < max_it; ++it) {
-      const bool v0 = tile_of(0, it) < n_tiles, v1 = tile_of(1, it) < n_tiles;
-      if (!v0) break;
+    if (leader) {
+      // ============================== MMA issuer ==============================
+      long long pa = 0, pw = 0, pp = 0;
+      const long long tstart = clock64();
+      for (long long it = 0; it < max_it; ++it) {
 #pragma unroll 1
-      for (int s = 0; s < kFwdSteps; ++s) {
-        const uint32_t idesc = umma_idesc(128, fwd_n(s), 0, 0);
-        const int nkb = fwd_nkb(s);
-        if (!p.share_w) {
-          // ping-pong: slot 0's whole step, then slot 1's (its epilogue overlaps the other slot's MMAs)
+        for (int s = 0; s < kFwdSteps; ++s) {
+          const uint32_t idesc = umma_idesc(CTA2 ? 256 : 128, fwd_n(s), 0, 0);
+          const int nkb = fwd_nkb(s);
           for (int slot = 0; slot < 2; ++slot) {
-            if (slot == 1 && !v1) break;
-            { const long long t0 = clock64(); mbar_wait(b_aready + 8 * slot, par_a[slot]); pa += clock64() - t0; }
+            if (unit_of(slot, it) >= n_units) continue;
+            { const long long t0 = clock64();
+              if (CTA2) mbar_wait_cluster(b_aready + 8 * slot, par_a[slot]); else mbar_wait(b_aready + 8 * slot, par_a[slot]);
+              pa += clock64() - t0; }
             par_a[slot] ^= 1;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
             for (int kb = 0; kb < nkb; ++kb) {
-              { const long long t0 = clock64(); mbar_wait(b_wfull + 8 * stage, phase); pw += clock64() - t0; }
+              { const long long t0 = clock64(); mbar_wait(b_wfull + 8 * stage, phase); const long long t1 = clock64(); pw += t1 - t0;
+                if (CTA2) { mbar_wait_cluster(b_pfull + 8 * stage, phase); pp += clock64() - t1; } }
               tc_fence_after();
               if (lane == 0) {
                 const int src = fwd_a_src(s, kb);
                 const uint32_t a_addr = (src < 0) ? (s_aux + slot * kBlobBytes) : (s_act + slot * kActBytes + (uint32_t)src * kBlobBytes);
-                const uint32_t b_addr = s_w + stage * 32768u;
+                const uint32_t b_addr = s_w + stage * STAGE_BYTES;
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-                  umma_ss(d_tmem, umma_desc(a_addr + k4 * 32u, 16, 1024), umma_desc(b_addr + k4 * 32u, 16, 1024), idesc,
-                          (kb | k4) ? 1u : 0u);
-                umma_commit(b_wempty + 8 * stage);
-                if (kb == nkb - 1) umma_commit(b_accready + 8 * slot);
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  const uint64_t ad = umma_desc(a_addr + k4 * 32u, 16, 1024), bd = umma_desc(b_addr + k4 * 32u, 16, 1024);
+                  if (CTA2) umma_ss_2cta(d_tmem, ad, bd, idesc, (kb | k4) ? 1u : 0u);
+                  else umma_ss(d_tmem, ad, bd, idesc, (kb | k4) ? 1u : 0u);
+                }
+                if (CTA2) {
+                  umma_commit_2cta(b_wempty + 8 * stage);
+                  if (kb == nkb - 1) umma_commit_2cta(b_accready + 8 * slot);
+                } else {
+                  umma_commit(b_wempty + 8 * stage);                      // stage is free once these MMAs retire
+                  if (kb == nkb - 1) umma_commit(b_accready + 8 * slot);  // accumulator complete
+                }
               }
               __syncwarp();
-              stage ^= 1; if (stage == 0) phase ^= 1;
+              if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
           }
-          continue;
         }
-        mbar_wait(b_aready + 0, par_a[0]); par_a[0] ^= 1;
-        if (v1) { mbar_wait(b_aready + 8, par_a[1]); par_a[1] ^= 1; }
-        tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(b_wfull + 8 * stage, phase);
-          tc_fence_after();
-          if (lane == 0) {
-            const int src = fwd_a_src(s, kb);
-            const uint32_t b_addr = s_w + stage * 32768u;
-#pragma unroll
+      }
+      if (p.prof && lane == 0) {
+        long long* o = p.prof + (size_t)blockIdx.x * 8;
+        o[0] = pa; o[1] = pw; o[2] = pp; o[3] = clock64() - tstart;
+      }
+    } else {
+      // ============================== peer: forward "my half landed" to the leader ==============================
+      if (lane == 0) {
+        for (long long it = 0; it < max_it; ++it) {
+#pragma unroll 1
+          for (int s = 0; s < kFwdSteps; ++s)
             for (int slot = 0; slot < 2; ++slot) {
-              if (slot == 1 && !v1) break;
-              const uint32_t a_addr = (src < 0) ? (s_aux + slot * kBlobBytes) : (s_act + slot * kActBytes + (uint32_t)src * kBlobBytes);
-              const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
-#pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)
-                umma_ss(d_tmem, umma_desc(a_addr + k4 * 32u, 16, 1024), umma_desc(b_addr + k4 * 32u, 16, 1024), idesc,
-                        (kb | k4) ? 1u : 0u);
-              if (kb == nkb - 1) umma_commit(b_accready + 8 * slot);   // this slot's accumulator is complete
+              if (unit_of(slot, it) >= n_units) continue;
+              for (int kb = 0; kb < fwd_nkb(s); ++kb) {
+                mbar_wait(b_wfull + 8 * stage, phase);
+                mbar_arrive_cluster(mapa_u32(b_pfull + 8 * stage, 0));
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+              }
             }
-            umma_commit(b_wempty + 8 * stage);                         // stage is free once both slots' MMAs retire
-          }
-          __syncwarp();
-          stage ^= 1; if (stage == 0) phase ^= 1;
         }
       }
     }
-    if (p.prof && lane == 0) { p.prof[blockIdx.x * 8 + 1] = pa; p.prof[blockIdx.x * 8 + 2] = pw; p.prof[blockIdx.x * 8 + 3] = clock64() - tstart; }
   } else {
     // ============================== epilogue groups ==============================
     const int slot = (warp - 2) >> 2;
@@ -330,17 +345,21 @@ mlp_fwd_chain_kernel(const FwdParams p) {
     const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + (uint32_t)slot * 256u;
     const int grp_tid = threadIdx.x - (64 + slot * 128);    // 0..127 inside the epilogue group
     const int bar_id = kBarEpi0 + slot;
+    const uint32_t a_ready_addr = CTA2 ? mapa_u32(b_aready + 8 * slot, 0) : 0u;   // the LEADER's barrier
     uint32_t par_acc = 0;
     bool store_pending = false;                              // a bulk store issued by grp_tid 0 still reads smem
-    long long pe_wait = 0, pe_body = 0, pe_pro = 0;
+
     for (long long it = 0; it < max_it; ++it) {
-      const long long tile = tile_of(slot, it);
-      if (tile >= n_tiles) break;
+      const long long unit = unit_of(slot, it);
+      if (unit >= n_units) break;
+      const long long tile = CTA2 ? unit * 2 + rank : unit;
+      const bool tile_ok = tile < n_tiles;                  // CTA2: the last pair may have a ghost second tile
       const long long pt = tile * 128 + r;
       const bool valid = pt < p.P;
       const long long pc = valid ? pt : p.P - 1;            // clamp: padded rows compute finite garbage
       // ---- layer-0 operand: positional encoding of the point (K3 fused) ----
       float dirx = 0.f, diry = 0.f, dirz = 0.f;
+      if (TRAIN && store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, 128); store_pending = false; }
       if (p.x_emb == nullptr) {
         const long long ray = pc / p.S;
         const float* rr = p.rays + ray * 6;
@@ -348,28 +367,24 @@ mlp_fwd_chain_kernel(const FwdParams p) {
         const float ox = rr[0], oy = rr[1], oz = rr[2], dx = rr[3], dy = rr[4], dz = rr[5];
         const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
         dirx = dx * inv; diry = dy * inv; dirz = dz * inv;
-        if (TRAIN && store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, 128); store_pending = false; }
         pe_row_to_smem<10>(aux_base + r * 128u, r, fmaf(dx, zz, ox), fmaf(dy, zz, oy), fmaf(dz, zz, oz), false);
       } else {
-        if (TRAIN && store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, 128); store_pending = false; }
         emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x, 63, false);
       }
       fence_proxy_async_smem();
       if (TRAIN) {
         named_bar_sync(bar_id, 128);
-        if (grp_tid == 0) { bulk_s2g(p.stash + p.st.off_embx + (size_t)tile * kBlobBytes, aux_base, kBlobBytes); bulk_commit(); }
+        if (grp_tid == 0 && tile_ok) { bulk_s2g(p.stash + p.st.off_embx + (size_t)tile * kBlobBytes, aux_base, kBlobBytes); bulk_commit(); }
         store_pending = true;
       }
-      mbar_arrive(b_aready + 8 * slot);
+      if (CTA2) mbar_arrive_cluster(a_ready_addr); else mbar_arrive(b_aready + 8 * slot);
 
       float sigma = 0.f;
       float rgb[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int s = 0; s < kFwdSteps; ++s) {
-        long long t_e0 = clock64();
         mbar_wait(b_accready + 8 * slot, par_acc); par_acc ^= 1;
         tc_fence_after();
-        { const long long t1 = clock64(); pe_wait += t1 - t_e0; t_e0 = t1; }
         if (TRAIN && store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, 128); store_pending = false; }
         // The chunk loop is deliberately NOT unrolled and is specialised per step kind: one 32-column body is
         // ~200 instructions (3 KB) and stays resident in the instruction cache across chunks, steps and tiles.  (A fully
@@ -377,11 +392,12 @@ mlp_fwd_chain_kernel(const FwdParams p) {
         const int kind = (s == 7) ? 1 : (s == 9 ? 2 : (s == 8 ? 3 : 0));
         uint32_t* mdst = nullptr;
         if (TRAIN && s != 8)
-          mdst = reinterpret_cast<uint32_t*>(p.stash + p.st.off_mask) + (((size_t)tile * 9 + (s < 8 ? s : 8)) * 128 + r) * 8;
-        if (kind == 0) epi_chunks<TRAIN, DBG, 0>(p, s, 8, t_addr, act_base, r, pt, valid, mdst, sigma, rgb);
-        else if (kind == 1) epi_chunks<TRAIN, DBG, 1>(p, s, 8, t_addr, act_base, r, pt, valid, mdst, sigma, rgb);
-        else if (kind == 2) epi_chunks<TRAIN, DBG, 2>(p, s, 4, t_addr, act_base, r, pt, valid, mdst, sigma, rgb);
-        else epi_chunks<TRAIN, DBG, 3>(p, s, 8, t_addr, act_base, r, pt, valid, mdst, sigma, rgb);
+          mdst = reinterpret_cast<uint32_t*>(p.stash + p.st.off_mask) + (((size_t)(tile_ok ? tile : 0) * 9 + (s < 8 ? s : 8)) * 128 + r) * 8;
+        const bool wmask = TRAIN && tile_ok;
+        if (kind == 0) epi_chunks<TRAIN, DBG, 0>(p, s, 8, t_addr, act_base, r, pt, valid, wmask ? mdst : nullptr, sigma, rgb);
+        else if (kind == 1) epi_chunks<TRAIN, DBG, 1>(p, s, 8, t_addr, act_base, r, pt, valid, wmask ? mdst : nullptr, sigma, rgb);
+        else if (kind == 2) epi_chunks<TRAIN, DBG, 2>(p, s, 4, t_addr, act_base, r, pt, valid, wmask ? mdst : nullptr, sigma, rgb);
+        else epi_chunks<TRAIN, DBG, 3>(p, s, 8, t_addr, act_base, r, pt, valid, nullptr, sigma, rgb);
         if (s == 5) {
           // the step-9 operand needs PE(viewdir) in aux; aux (PE of the point) was last read by MMA step 5, now retired
           if (p.x_emb == nullptr) pe_row_to_smem<4>(aux_base + r * 128u, r, dirx, diry, dirz, false);
@@ -391,7 +407,7 @@ mlp_fwd_chain_kernel(const FwdParams p) {
         tc_fence_before();
         if (TRAIN) {
           named_bar_sync(bar_id, 128);
-          if (grp_tid == 0 && !(p.abl & 2)) {
+          if (grp_tid == 0 && tile_ok) {
             const size_t off = (s < 8 ? p.st.off_h[s] : (s == 8 ? p.st.off_feat : p.st.off_g));
             const uint32_t nb = (s == 9) ? 2u : 4u;
             bulk_s2g(p.stash + off + (size_t)tile * nb * kBlobBytes, act_base, nb * kBlobBytes);
@@ -400,9 +416,8 @@ mlp_fwd_chain_kernel(const FwdParams p) {
           }
           store_pending = true;
         }
-        pe_body += clock64() - t_e0;
         if (s < 9) {
-          mbar_arrive(b_aready + 8 * slot);
+          if (CTA2) mbar_arrive_cluster(a_ready_addr); else mbar_arrive(b_aready + 8 * slot);
         } else if (valid) {
           const float4 bc = make_float4(c_fw.bc[0], c_fw.bc[1], c_fw.bc[2], c_fw.bc[3]);
           reinterpret_cast<float4*>(p.raw)[pt] = make_float4(rgb[0] + bc.x, rgb[1] + bc.y, rgb[2] + bc.z, sigma + bc.w);
@@ -410,12 +425,11 @@ mlp_fwd_chain_kernel(const FwdParams p) {
       }
     }
     if (TRAIN && store_pending && grp_tid == 0) bulk_wait_all0();
-    if (p.prof && grp_tid == 0) { p.prof[blockIdx.x * 8 + 4 + slot * 2] = pe_wait; p.prof[blockIdx.x * 8 + 5 + slot * 2] = pe_body; }
-    (void)pe_pro;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (CTA2) cluster_sync_all();      // nobody exits while the partner may still signal its barriers / read its smem
+  if (warp == 1) { if (CTA2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -534,18 +548,43 @@ int nb_tc_pack(nb_handle_t h, const nb_mlp_desc* d, const float* params, void* p
 }
 
 static int launch_fwd(nb_handle_t h, FwdParams& fp, bool train, cudaStream_t st) {
-  static bool attr_done[3] = {false, false, false};
+  static bool attr_done[6] = {false, false, false, false, false, false};
   const bool dbg = fp.dbg != nullptr;
-  auto kern = dbg ? mlp_fwd_chain_kernel<false, true> : (train ? mlp_fwd_chain_kernel<true, false> : mlp_fwd_chain_kernel<false, false>);
-  const int ki = dbg ? 2 : (train ? 1 : 0);
+  static int cta2_env = -1;
+  if (cta2_env < 0) { const char* e = getenv("NB_TC_CTA2"); cta2_env = e ? atoi(e) : 0; }   // measured: pairs help only the weight stream
+  const bool cta2 = cta2_env != 0;
+  typedef void (*kern_t)(const FwdParams);
+  kern_t kern;
+  if (cta2) kern = dbg ? mlp_fwd_chain_kernel<false, true, true> : (train ? mlp_fwd_chain_kernel<true, false, true> : mlp_fwd_chain_kernel<false, false, true>);
+  else kern = dbg ? mlp_fwd_chain_kernel<false, true, false> : (train ? mlp_fwd_chain_kernel<true, false, false> : mlp_fwd_chain_kernel<false, false, false>);
+  const int ki = (dbg ? 2 : (train ? 1 : 0)) + (cta2 ? 3 : 0);
   if (!attr_done[ki]) {
     NB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr_done[ki] = true;
   }
   NB_CUDA(h, cudaMemcpyToSymbolAsync(c_fw, fp.wpk + nb_tc_small_offset(), sizeof(TcSmall), 0, cudaMemcpyDeviceToDevice, st));
   const long long n_tiles = (fp.P + 127) / 128;
-  long long grid = (n_tiles + 1) / 2;
-  if (grid > h->sm_count) grid = h->sm_count;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  if (cta2) {
+    const long long n_pairs = (n_tiles + 1) / 2;
+    long long ncl = (n_pairs + 1) / 2;                       // two pair-tiles (slots) per cluster
+    const long long max_cl = h->sm_count / 2;
+    if (ncl > max_cl) ncl = max_cl;
+    if (ncl < 1) ncl = 1;
+    cfg.gridDim = dim3((unsigned)(2 * ncl));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  } else {
+    long long grid = (n_tiles + 1) / 2;
+    if (grid > h->sm_count) grid = h->sm_count;
+    cfg.gridDim = dim3((unsigned)grid);
+  }
   static long long* prof_dev = nullptr;
   const bool prof = getenv("NB_TC_PROF") != nullptr;
   if (prof) {
@@ -553,17 +592,16 @@ static int launch_fwd(nb_handle_t h, FwdParams& fp, bool train, cudaStream_t st)
     cudaMemsetAsync(prof_dev, 0, 256 * 8 * sizeof(long long), st);
     fp.prof = prof_dev;
   }
-  kern<<<(int)grid, kThreads, kSmemBytes, st>>>(fp);
+  NB_CUDA(h, cudaLaunchKernelEx(&cfg, kern, fp));
   NB_LAUNCHED(h);
-  if (prof) {   // diagnostic only: synchronous read-back of the per-CTA cycle counters
+  if (prof) {   // diagnostic only: synchronous read-back of the MMA warp's cycle counters
     static long long host[256 * 8];
     cudaStreamSynchronize(st);
     cudaMemcpy(host, prof_dev, sizeof(host), cudaMemcpyDeviceToHost);
-    double a[8] = {0};
-    for (int b = 0; b < grid; ++b) for (int k = 0; k < 8; ++k) a[k] += (double)host[b * 8 + k] / grid;
-    fprintf(stderr, "nb_tc prof (avg cycles/CTA, P=%lld train=%d): epi1_tmem_ld=%.0f mma_wait_aready=%.0f mma_wait_wfull=%.0f "
-            "mma_total=%.0f epi0_wait=%.0f epi0_body=%.0f epi1_wait=%.0f epi1_body=%.0f\n", fp.P, (int)train, a[0], a[1], a[2], a[3],
-            a[4], a[5], a[6], a[7]);
+    double a[4] = {0}; int n = 0;
+    for (unsigned b = 0; b < cfg.gridDim.x; ++b) if (host[b * 8 + 3] > 0) { ++n; for (int k = 0; k < 4; ++k) a[k] += (double)host[b * 8 + k]; }
+    fprintf(stderr, "nb_tc prof P=%lld train=%d cta2=%d: mma_wait_aready=%.0f mma_wait_wfull=%.0f mma_wait_peerfull=%.0f mma_total=%.0f\n",
+            fp.P, (int)train, (int)cta2, a[0] / n, a[1] / n, a[2] / n, a[3] / n);
   }
   return NB_OK;
 }
@@ -578,8 +616,7 @@ int nb_tc_forward(nb_handle_t h, const nb_mlp_desc* d, const float* params, cons
   fp.wpk = (const uint8_t*)packed; fp.prm = params; fp.L = nb_param_layout(*d); fp.raw = raw_out;
   fp.stash = (uint8_t*)act_save; fp.st = nb_tc_stash_layout(P);
   fp.dbg = nullptr; fp.dbg_step = -1;
-  { const char* e = getenv("NB_TC_ABLATE"); fp.abl = e ? atoi(e) : 0; }
-  { const char* e = getenv("NB_TC_SHARE_W"); fp.share_w = e ? atoi(e) : 0; }
+  fp.abl = 0;
   return launch_fwd(h, fp, act_save != nullptr, st);
 }
 

@@ -14,7 +14,7 @@ struct TcStash {
   size_t off_h[8];             // post-ReLU trunk outputs h0..h7                   : 4 blobs / tile
   size_t off_feat;             // feature layer output                             : 4 blobs / tile
   size_t off_g;                // post-ReLU view layer output (128 wide)           : 2 blobs / tile
-  size_t off_mask;             // ReLU masks: [tile][9 = h0..h7, g][128 rows][8 x u32], bit j of word c = column 32c+j > 0
+  size_t off_mask;             // ReLU masks: [tile][9 = h0..h7, g][128 rows][8 x u32], bit (31-j) of word c = sign bit of column 32c+j (set = inactive)
   size_t total;
   long long tiles;
 };

@@ -187,7 +187,7 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
           const int col = c * 8 + j;
           const float val = fmaf(dr.x, c_bw.wc[col], fmaf(dr.y, c_bw.wc[128 + col], dr.z * c_bw.wc[256 + col]));
           const uint32_t gmsel = (c & 8) ? ((c & 4) ? gmw[3] : gmw[2]) : ((c & 4) ? gmw[1] : gmw[0]);
-          v[j] = ((gmsel >> (col & 31)) & 1u) ? val : 0.f;
+          v[j] = ((gmsel >> (31 - (col & 31))) & 1u) ? 0.f : val;
         }
         st_shared_v4(act_base + (uint32_t)(c >> 3) * kBlobBytes + sw128_chunk(r, (uint32_t)(c & 7)), pack_bf16(v[0], v[1]),
                      pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -212,7 +212,7 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
 #pragma unroll 1
       for (int b = 0; b < kBwdSteps; ++b) {
         // ReLU mask of h_{8-b} for this step (b >= 1): 8 words per row, fetched while the MMA runs
-        uint32_t mq[8] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
+        uint32_t mq[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};      // set bit = inactive unit
         if (b >= 1) {
           const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)(8 - b) * 128 * 8));
           const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)(8 - b) * 128 * 8) + 1);
@@ -239,7 +239,7 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
             const uint32_t m = (c32 & 4) ? m47 : m03;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (!((m >> j) & 1u)) v[j] = 0.f;
+              if ((m >> (31 - j)) & 1u) v[j] = 0.f;
           }
           const uint32_t row_addr = act_base + (uint32_t)(c32 >> 1) * kBlobBytes + r * 128u;
 #pragma unroll

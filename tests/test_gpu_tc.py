@@ -165,9 +165,9 @@ def decode_blobs(buf, off, tiles, nblk):
 
 
 def decode_masks(buf, off, tiles):
-    """[tiles][9][128][8 x u32] -> bool [9, tiles*128, 256]."""
+    """[tiles][9][128][8 x u32] -> bool "active" [9, tiles*128, 256]; bit (31-j) of word c is the SIGN of column 32c+j."""
     w = buf[off:off + tiles * 9 * 128 * 32].view(np.uint32).reshape(tiles, 9, 128, 8)
-    bits = ((w[..., None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool).reshape(tiles, 9, 128, 256)
+    bits = (((w[..., None] >> (31 - np.arange(32, dtype=np.uint32))) & 1) == 0).reshape(tiles, 9, 128, 256)
     return bits.transpose(1, 0, 2, 3).reshape(9, tiles * 128, 256)
 
 
