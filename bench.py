@@ -307,7 +307,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         for i in range(n_fr):
             rgb, disp = trainer.render_frame(model, H, W, K, poses_dev[i % len(poses), :3, :4], opts, dist_ctx=dctx)
-            frame8 = (rgb.clamp(0, 1) * 255).to(torch.uint8).cpu()          # D2H of the finished frame
+            frame8 = eng.frame_to8b(rgb, disp)[0].cpu()                      # to8b on device + D2H of the finished frame
         barrier()
         fr_ms = (time.perf_counter() - t0) * 1e3 / n_fr
         t = torch.tensor([fr_ms], device=dev)

@@ -182,6 +182,12 @@ int nb_mse_grad(nb_handle_t h, int64_t N, const float* rgb, const float* target,
 int nb_adam_step(nb_handle_t h, int64_t n, float* p, const float* g, float* m, float* v, float lr, float beta1,
                  float beta2, float eps, int32_t step, void* stream);
 
+/* ---- frame output ---------------------------------------------------------- */
+/* test.py:50-61 / utils.py:11: rgb8[N,3] = to8b(rgb), disp8[N] = to8b(disp / nanmax(disp)) on the device.
+ * disp8 may be NULL (rgb only); disp_max_scratch is one device float used for the nanmax reduction. */
+int nb_frame_to8b(nb_handle_t h, int64_t N, const float* rgb, const float* disp, float* disp_max_scratch,
+                  uint8_t* rgb8, uint8_t* disp8, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -55,6 +55,7 @@ SIGNATURES = {
     'nb_mlp_tc_probe': (C.c_int, [_p, _desc, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p]),
     'nb_composite_forward': (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'nb_composite_backward': (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p]),
+    'nb_frame_to8b': (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p]),
     'nb_mse_grad': (C.c_int, [_p, _i64, _p, _p, _f32, _f32, _p, _p, _p]),
     'nb_adam_step': (C.c_int, [_p, _i64, _p, _p, _p, _p, _f32, _f32, _f32, _f32, _i32, _p]),
 }

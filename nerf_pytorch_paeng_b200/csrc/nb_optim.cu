@@ -46,7 +46,56 @@ adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, flo
   }
 }
 
+// frame output (test.py:50-61, utils.py:11): rgb8 = to8b(rgb), disp8 = to8b(disp / nanmax(disp))
+__global__ void __launch_bounds__(256)
+nanmax_kernel(long long n, const float* __restrict__ x, float* __restrict__ out) {
+  float m = 0.f;   // disparities are >= 0; NaNs are skipped like np.nanmax
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    if (v == v) m = fmaxf(m, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));   // valid for non-negative floats
+}
+
+__device__ __forceinline__ unsigned char to8b_dev(float x) {
+  // (255*np.clip(x,0,1)).astype(np.uint8): truncation towards zero; NaN -> 0
+  if (!(x == x)) return 0;
+  return (unsigned char)(255.0f * fminf(fmaxf(x, 0.f), 1.f));
+}
+
+__global__ void __launch_bounds__(256)
+frame8_kernel(long long n, const float* __restrict__ rgb, const float* __restrict__ disp, const float* __restrict__ disp_max,
+              unsigned char* __restrict__ rgb8, unsigned char* __restrict__ disp8) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float dm = disp_max ? *disp_max : 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * 3; i += stride) rgb8[i] = to8b_dev(rgb[i]);
+  if (disp && disp8)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) disp8[i] = to8b_dev(disp[i] / dm);
+}
+
 }  // namespace
+
+extern "C" int nb_frame_to8b(nb_handle_t h, int64_t N, const float* rgb, const float* disp, float* disp_max_scratch,
+                             uint8_t* rgb8, uint8_t* disp8, void* stream) {
+  NB_ENTER(h);
+  if (N == 0) return NB_OK;
+  NB_REQUIRE(h, N > 0 && rgb && rgb8 && (!disp8 || (disp && disp_max_scratch)), "nb_frame_to8b: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)((N + 255) / 256);
+  const int cap = h->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (disp8) {
+    NB_CUDA(h, cudaMemsetAsync(disp_max_scratch, 0, sizeof(float), st));
+    nanmax_kernel<<<blocks, 256, 0, st>>>((long long)N, disp, disp_max_scratch);
+    NB_LAUNCHED(h);
+  }
+  frame8_kernel<<<blocks, 256, 0, st>>>((long long)N, rgb, disp8 ? disp : nullptr, disp8 ? disp_max_scratch : nullptr, rgb8, disp8);
+  NB_LAUNCHED(h);
+  return NB_OK;
+}
 
 extern "C" int nb_mse_grad(nb_handle_t h, int64_t N, const float* rgb, const float* target, float scale, float loss_scale,
                            float* d_rgb, float* loss_out, void* stream) {

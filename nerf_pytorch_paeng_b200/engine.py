@@ -241,6 +241,19 @@ class Engine:
         self._call('nb_composite_backward', n, s, _ptr(raw), _ptr(z), _ptr(rays_d), _ptr(d_rgb), _ptr(d_raw), self.stream)
         return d_raw
 
+    def frame_to8b(self, rgb, disp=None):
+        """test.py:50-61: uint8 frame (and disparity normalised by its nanmax) on the device."""
+        rgb = _chk32(rgb, 'rgb')
+        n = rgb.shape[0] if rgb.dim() == 2 else rgb.numel() // 3
+        rgb8 = torch.empty(rgb.shape, dtype=torch.uint8, device=self.device)
+        disp8 = scratch = None
+        if disp is not None:
+            disp = _chk32(disp, 'disp')
+            disp8 = torch.empty(disp.shape, dtype=torch.uint8, device=self.device)
+            scratch = self.empty(1)
+        self._call('nb_frame_to8b', n, _ptr(rgb), _ptr(disp), _ptr(scratch), _ptr(rgb8), _ptr(disp8), self.stream)
+        return rgb8, disp8
+
     # ------------------------------------------------------------------ loss / optimiser
     def mse_grad(self, rgb, target, scale, loss_scale=0., loss_out=None, want_grad=True):
         rgb = _chk32(rgb, 'rgb')

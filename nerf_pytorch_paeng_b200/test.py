@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 from . import trainer
+from .engine import get_engine
 from .config import LOG_DIR
 from .utils import img2mse, mse2psnr, to8b
 
@@ -37,12 +38,12 @@ def test(idx, i_test, posenc, model, test_imgs, gt_intrinsic, gt_extrinsic, hw, 
         gt = torch.as_tensor(test_imgs[i], dtype=torch.float32).to(rgb.device)
         psnr = mse2psnr(img2mse(rgb, gt).reshape(1))
         psnrs.append(float(psnr))
-        rgb8 = to8b(rgb.cpu().numpy())
-        disp_np = disp.cpu().numpy()
+        rgb8_d, disp8_d = get_engine(rgb.device).frame_to8b(rgb, disp)      # to8b + disp/nanmax(disp) on the device
+        rgb8 = rgb8_d.cpu().numpy()
         frames.append(rgb8)
         if save:
             _imwrite(out_dir, '{:03d}.png'.format(i), rgb8)
-            _imwrite(out_dir, '{:03d}_disp.png'.format(i), to8b(disp_np / max(np.nanmax(disp_np), 1e-10)))
+            _imwrite(out_dir, '{:03d}_disp.png'.format(i), disp8_d.cpu().numpy())
         print('idx:{} | PSNR:{}'.format(i, psnrs[-1]))
     return {'psnr': psnrs, 'frames': frames}
 
@@ -53,9 +54,9 @@ def render(idx, posenc, model, gt_intrinsic, render_pose, hw, opts, dist_ctx=Non
     out_dir = os.path.join(LOG_DIR, opts.exp_name, opts.exp_name + '_{}'.format(idx), 'render_result')
     rgbs, disps = [], []
     for i, (rgb, disp) in enumerate(_frames(model, render_pose, gt_intrinsic, hw, opts, dist_ctx)):
-        rgb_np, disp_np = rgb.cpu().numpy(), disp.cpu().numpy()
-        rgbs.append(to8b(rgb_np))
-        disps.append(to8b(disp_np / max(np.nanmax(disp_np), 1e-10)))
+        rgb8_d, disp8_d = get_engine(rgb.device).frame_to8b(rgb, disp)
+        rgbs.append(rgb8_d.cpu().numpy())
+        disps.append(disp8_d.cpu().numpy())
         if save:
             _imwrite(out_dir, f'{i}_rgb.png', rgbs[-1])
             _imwrite(out_dir, f'{i}_disp.png', disps[-1])
