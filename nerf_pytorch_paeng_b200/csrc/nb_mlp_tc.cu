@@ -56,7 +56,11 @@ constexpr uint32_t kOffW = kOffAux + 2 * kBlobBytes;         // [2][32 KB]
 constexpr uint32_t kOffBar = kOffW + 2 * 32768;              // barriers (256 B)
 constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;        // + alignment slack
 
-constexpr int kThreads = 320;
+constexpr int kThreads = 576;   // warp 0 producer, warp 1 MMA, 8 epilogue warps per slot (2 per TMEM lane quarter: column halves)
+constexpr int kEpiThreads = 256;
+// measured: per-thread 16-byte stash stores (stride 128 B) free the TMA unit for the weight stream (wait_wfull 45% -> 14%)
+// but triple the epilogue time; the activation tile is therefore bulk-stored from shared memory, in 16 KB pieces.
+constexpr bool kDirectStash = false;
 constexpr int kBarEpi0 = 1;
 
 __constant__ TcSmall c_fw;   // small fp32 parameters of the network being run (see nb_mlp_tc.h)   // named barrier ids of the two epilogue groups
@@ -84,7 +88,7 @@ struct FwdParams {
 // Arguments are reduced in "turns": sin(2^k x) = sin(2 pi frac(2^k x / 2 pi)), exact power-of-two scaling,
 // so the fast sin.approx/cos.approx see |arg| <= pi (abs error ~1e-6, far below a bf16 ulp).
 template <int L>
-__device__ __forceinline__ void pe_row_to_smem(uint32_t row_addr, uint32_t r, float x, float y, float z, bool one_pad) {
+__device__ __forceinline__ void pe_row_to_smem(uint32_t row_addr, uint32_t r, float x, float y, float z, bool one_pad, int c_lo, int c_hi) {
   constexpr int NF = 3 + 6 * L;
   constexpr int NCH = (NF + 8) / 8;          // chunks that hold features (+ the optional 1.0 pad column)
   float e[NCH * 8];
@@ -113,14 +117,14 @@ __device__ __forceinline__ void pe_row_to_smem(uint32_t row_addr, uint32_t r, fl
       w0 = pack_bf16(e[c * 8 + 0], e[c * 8 + 1]); w1 = pack_bf16(e[c * 8 + 2], e[c * 8 + 3]);
       w2 = pack_bf16(e[c * 8 + 4], e[c * 8 + 5]); w3 = pack_bf16(e[c * 8 + 6], e[c * 8 + 7]);
     }
-    st_shared_v4(row_addr + (((uint32_t)c ^ (r & 7u)) << 4), w0, w1, w2, w3);
+    if (c >= c_lo && c < c_hi) st_shared_v4(row_addr + (((uint32_t)c ^ (r & 7u)) << 4), w0, w1, w2, w3);   // this thread's column half
   }
 }
 
 // copy 64 bf16 features (cols [c0, c0+ncol) of a materialised fp32 embedding row) into a swizzled row
-__device__ __forceinline__ void emb_row_to_smem(uint32_t row_addr, uint32_t r, const float* src, int ncol, bool one_pad) {
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
+__device__ __forceinline__ void emb_row_to_smem(uint32_t row_addr, uint32_t r, const float* src, int ncol, bool one_pad, int c_lo, int c_hi) {
+#pragma unroll 1
+  for (int c = c_lo; c < c_hi; ++c) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -136,11 +140,11 @@ __device__ __forceinline__ void emb_row_to_smem(uint32_t row_addr, uint32_t r, c
 // KIND 0: bias+ReLU -> bf16 A tile | 1: same + sigma head (step 7) | 2: view layer + rgb head (step 9; A tile only
 // written in training, for the stash) | 3: feature layer, no activation (step 8).
 template <bool TRAIN, bool DBG, int KIND>
-__device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int nchunks, uint32_t t_addr, uint32_t act_base, uint32_t r,
-                                           long long pt, bool valid, uint32_t* mdst, float& sigma, float (&rgb)[3]) {
+__device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begin, int c_end, uint32_t t_addr, uint32_t act_base, uint32_t r,
+                                           long long pt, bool valid, uint32_t* mdst, uint8_t* gdst, float& sigma, float (&rgb)[3]) {
   const float* bias = c_fw.bias[s];
 #pragma unroll 1
-  for (int c32 = 0; c32 < nchunks; ++c32) {
+  for (int c32 = c_begin; c32 < c_end; ++c32) {
     float v[32];
     tmem_ld32(t_addr + (uint32_t)c32 * 32u, v);
     tmem_ld_wait();
@@ -190,6 +194,10 @@ __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int nchunk
           w2 = pack_bf16_relu(v[j * 8 + 4], v[j * 8 + 5]); w3 = pack_bf16_relu(v[j * 8 + 6], v[j * 8 + 7]);
         }
         st_shared_v4(row_addr + ((c ^ (r & 7u)) << 4), w0, w1, w2, w3);
+        // training: the same 16 bytes go straight to the stash blob (same swizzled image).  Direct stores keep the
+        // TMA unit and the shared-memory read port free for the weight stream and the MMA operands.
+        if (TRAIN && kDirectStash && gdst != nullptr)
+          *reinterpret_cast<uint4*>(gdst + (size_t)(c32 >> 1) * kBlobBytes + r * 128u + ((c ^ (r & 7u)) << 4)) = make_uint4(w0, w1, w2, w3);
       }
     }
   }
@@ -231,7 +239,7 @@ mlp_fwd_chain_kernel(const FwdParams p) {
       mbar_init(b_pfull + 8 * i, 1);
     }
     for (uint32_t i = 0; i < 2; ++i) {
-      mbar_init(b_aready + 8 * i, CTA2 ? 256 : 128);
+      mbar_init(b_aready + 8 * i, CTA2 ? 2 * kEpiThreads : kEpiThreads);
       mbar_init(b_accready + 8 * i, 1);
     }
     fence_barrier_init();
@@ -338,16 +346,18 @@ mlp_fwd_chain_kernel(const FwdParams p) {
     }
   } else {
     // ============================== epilogue groups ==============================
-    const int slot = (warp - 2) >> 2;
+    const int slot = (warp - 2) >> 3;
+    const int half = ((warp - 2) >> 2) & 1;                 // which half of the accumulator columns this warp drains
     const uint32_t q = (uint32_t)warp & 3u;                 // TMEM lane quarter this warp may access
-    const uint32_t r = q * 32u + (uint32_t)lane;            // row of the tile = point
+    const uint32_t r = q * 32u + (uint32_t)lane;            // row of the tile = point (two threads per row: column halves)
     const uint32_t act_base = s_act + slot * kActBytes, aux_base = s_aux + slot * kBlobBytes;
     const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + (uint32_t)slot * 256u;
-    const int grp_tid = threadIdx.x - (64 + slot * 128);    // 0..127 inside the epilogue group
+    const int grp_tid = threadIdx.x - (64 + slot * kEpiThreads);    // 0..255 inside the epilogue group
     const int bar_id = kBarEpi0 + slot;
     const uint32_t a_ready_addr = CTA2 ? mapa_u32(b_aready + 8 * slot, 0) : 0u;   // the LEADER's barrier
     uint32_t par_acc = 0;
     bool store_pending = false;                              // a bulk store issued by grp_tid 0 still reads smem
+    long long pe_wait = 0, pe_body = 0, pe_pro = 0;
 
     for (long long it = 0; it < max_it; ++it) {
       const long long unit = unit_of(slot, it);
@@ -359,7 +369,8 @@ mlp_fwd_chain_kernel(const FwdParams p) {
       const long long pc = valid ? pt : p.P - 1;            // clamp: padded rows compute finite garbage
       // ---- layer-0 operand: positional encoding of the point (K3 fused) ----
       float dirx = 0.f, diry = 0.f, dirz = 0.f;
-      if (TRAIN && store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, 128); store_pending = false; }
+      const long long t_p0 = clock64();
+      if (TRAIN && store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, kEpiThreads); store_pending = false; }
       if (p.x_emb == nullptr) {
         const long long ray = pc / p.S;
         const float* rr = p.rays + ray * 6;
@@ -367,25 +378,28 @@ mlp_fwd_chain_kernel(const FwdParams p) {
         const float ox = rr[0], oy = rr[1], oz = rr[2], dx = rr[3], dy = rr[4], dz = rr[5];
         const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
         dirx = dx * inv; diry = dy * inv; dirz = dz * inv;
-        pe_row_to_smem<10>(aux_base + r * 128u, r, fmaf(dx, zz, ox), fmaf(dy, zz, oy), fmaf(dz, zz, oz), false);
+        pe_row_to_smem<10>(aux_base + r * 128u, r, fmaf(dx, zz, ox), fmaf(dy, zz, oy), fmaf(dz, zz, oz), false, half * 4, half * 4 + 4);
       } else {
-        emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x, 63, false);
+        emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x, 63, false, half * 4, half * 4 + 4);
       }
       fence_proxy_async_smem();
       if (TRAIN) {
-        named_bar_sync(bar_id, 128);
+        named_bar_sync(bar_id, kEpiThreads);
         if (grp_tid == 0 && tile_ok) { bulk_s2g(p.stash + p.st.off_embx + (size_t)tile * kBlobBytes, aux_base, kBlobBytes); bulk_commit(); }
         store_pending = true;
       }
       if (CTA2) mbar_arrive_cluster(a_ready_addr); else mbar_arrive(b_aready + 8 * slot);
+      pe_pro += clock64() - t_p0;
 
       float sigma = 0.f;
       float rgb[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int s = 0; s < kFwdSteps; ++s) {
+        long long t_e0 = clock64();
         mbar_wait(b_accready + 8 * slot, par_acc); par_acc ^= 1;
         tc_fence_after();
-        if (TRAIN && store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, 128); store_pending = false; }
+        { const long long t1 = clock64(); pe_wait += t1 - t_e0; t_e0 = t1; }
+        if (TRAIN && store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, kEpiThreads); store_pending = false; }
         // The chunk loop is deliberately NOT unrolled and is specialised per step kind: one 32-column body is
         // ~200 instructions (3 KB) and stays resident in the instruction cache across chunks, steps and tiles.  (A fully
         // unrolled epilogue streamed ~30 KB of code per step through the I-cache and ran 5x slower: stall_no_inst.)
@@ -394,37 +408,67 @@ mlp_fwd_chain_kernel(const FwdParams p) {
         if (TRAIN && s != 8)
           mdst = reinterpret_cast<uint32_t*>(p.stash + p.st.off_mask) + (((size_t)(tile_ok ? tile : 0) * 9 + (s < 8 ? s : 8)) * 128 + r) * 8;
         const bool wmask = TRAIN && tile_ok;
-        if (kind == 0) epi_chunks<TRAIN, DBG, 0>(p, s, 8, t_addr, act_base, r, pt, valid, wmask ? mdst : nullptr, sigma, rgb);
-        else if (kind == 1) epi_chunks<TRAIN, DBG, 1>(p, s, 8, t_addr, act_base, r, pt, valid, wmask ? mdst : nullptr, sigma, rgb);
-        else if (kind == 2) epi_chunks<TRAIN, DBG, 2>(p, s, 4, t_addr, act_base, r, pt, valid, wmask ? mdst : nullptr, sigma, rgb);
-        else epi_chunks<TRAIN, DBG, 3>(p, s, 8, t_addr, act_base, r, pt, valid, nullptr, sigma, rgb);
+        const int c0 = half * 4, c1 = half * 4 + 4;            // this warp's 128 of the 256 columns (64 of 128 at step 9)
+        uint8_t* gdst = nullptr;
+        if (TRAIN && tile_ok) {
+          const size_t off = (s < 8 ? p.st.off_h[s] : (s == 8 ? p.st.off_feat : p.st.off_g));
+          gdst = p.stash + off + (size_t)tile * (s == 9 ? 2u : 4u) * kBlobBytes;
+        }
+        if (kind == 0) epi_chunks<TRAIN, DBG, 0>(p, s, c0, c1, t_addr, act_base, r, pt, valid, wmask ? mdst : nullptr, gdst, sigma, rgb);
+        else if (kind == 1) epi_chunks<TRAIN, DBG, 1>(p, s, c0, c1, t_addr, act_base, r, pt, valid, wmask ? mdst : nullptr, gdst, sigma, rgb);
+        else if (kind == 2) epi_chunks<TRAIN, DBG, 2>(p, s, half * 2, half * 2 + 2, t_addr, act_base, r, pt, valid, wmask ? mdst : nullptr, gdst, sigma, rgb);
+        else epi_chunks<TRAIN, DBG, 3>(p, s, c0, c1, t_addr, act_base, r, pt, valid, nullptr, gdst, sigma, rgb);
+        // heads: the two column halves of a row exchange their partial rgb / sigma sums through a scratch row in the
+        // (now idle) fourth K-block of the activation tile
+        const uint32_t scratch = act_base + 3u * kBlobBytes + r * 16u;
+        if (s == 9 && half == 1)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(scratch), "f"(rgb[0]), "f"(rgb[1]), "f"(rgb[2]), "f"(sigma) : "memory");
         if (s == 5) {
           // the step-9 operand needs PE(viewdir) in aux; aux (PE of the point) was last read by MMA step 5, now retired
-          if (p.x_emb == nullptr) pe_row_to_smem<4>(aux_base + r * 128u, r, dirx, diry, dirz, false);
-          else emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x + 63, 27, false);
+          if (p.x_emb == nullptr) pe_row_to_smem<4>(aux_base + r * 128u, r, dirx, diry, dirz, false, half * 4, half * 4 + 4);
+          else emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x + 63, 27, false, half * 4, half * 4 + 4);
         }
         fence_proxy_async_smem();
         tc_fence_before();
         if (TRAIN) {
-          named_bar_sync(bar_id, 128);
-          if (grp_tid == 0 && tile_ok) {
-            const size_t off = (s < 8 ? p.st.off_h[s] : (s == 8 ? p.st.off_feat : p.st.off_g));
-            const uint32_t nb = (s == 9) ? 2u : 4u;
-            bulk_s2g(p.stash + off + (size_t)tile * nb * kBlobBytes, act_base, nb * kBlobBytes);
-            if (s == 5) bulk_s2g(p.stash + p.st.off_embd + (size_t)tile * kBlobBytes, aux_base, kBlobBytes);
-            bulk_commit();
+          named_bar_sync(bar_id, kEpiThreads);        // the whole A tile (both column halves) is in shared memory
+          if (s == 5) {                               // PE(viewdir) tile for wgrad: one 16 KB bulk store per tile
+            if (grp_tid == 0 && tile_ok) { bulk_s2g(p.stash + p.st.off_embd + (size_t)tile * kBlobBytes, aux_base, kBlobBytes); bulk_commit(); }
+            store_pending = true;
           }
-          store_pending = true;
         }
+        pe_body += clock64() - t_e0;
         if (s < 9) {
           if (CTA2) mbar_arrive_cluster(a_ready_addr); else mbar_arrive(b_aready + 8 * slot);
-        } else if (valid) {
-          const float4 bc = make_float4(c_fw.bc[0], c_fw.bc[1], c_fw.bc[2], c_fw.bc[3]);
-          reinterpret_cast<float4*>(p.raw)[pt] = make_float4(rgb[0] + bc.x, rgb[1] + bc.y, rgb[2] + bc.z, sigma + bc.w);
+        }
+        if (TRAIN && gdst != nullptr) {
+          // Activation stash: the tile is copied shared -> global by the epilogue threads themselves, fully coalesced
+          // (512 contiguous bytes per warp instruction), AFTER the MMA warp has been released, i.e. in the time this group
+          // would otherwise spend waiting for its next accumulator.  (A cp.async.bulk store here made the weight loads
+          // queue behind 64 KB of TMA traffic per step: the MMA issuer then waited 45% of its time for weight stages.)
+          const uint32_t n16 = ((s == 9) ? 2u : 4u) * (kBlobBytes / 16u);
+          for (uint32_t i = (uint32_t)grp_tid; i < n16; i += kEpiThreads) {
+            uint4 w;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(act_base + i * 16u));
+            asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gdst + (size_t)i * 16u), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+          }
+        }
+        if (s == 9) {
+          named_bar_sync(bar_id, kEpiThreads);                  // scratch rows of the other column half are visible
+          if (half == 0 && valid) {
+            float4 o;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(scratch));
+            reinterpret_cast<float4*>(p.raw)[pt] = make_float4(rgb[0] + o.x + c_fw.bc[0], rgb[1] + o.y + c_fw.bc[1],
+                                                               rgb[2] + o.z + c_fw.bc[2], sigma + o.w + c_fw.bc[3]);
+          }
         }
       }
     }
     if (TRAIN && store_pending && grp_tid == 0) bulk_wait_all0();
+    if (p.prof && grp_tid == 0 && slot == 0) {
+      long long* o = p.prof + (size_t)blockIdx.x * 8;
+      o[4] = pe_wait; o[5] = pe_body; o[6] = pe_pro;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -598,10 +642,11 @@ static int launch_fwd(nb_handle_t h, FwdParams& fp, bool train, cudaStream_t st)
     static long long host[256 * 8];
     cudaStreamSynchronize(st);
     cudaMemcpy(host, prof_dev, sizeof(host), cudaMemcpyDeviceToHost);
-    double a[4] = {0}; int n = 0;
-    for (unsigned b = 0; b < cfg.gridDim.x; ++b) if (host[b * 8 + 3] > 0) { ++n; for (int k = 0; k < 4; ++k) a[k] += (double)host[b * 8 + k]; }
-    fprintf(stderr, "nb_tc prof P=%lld train=%d cta2=%d: mma_wait_aready=%.0f mma_wait_wfull=%.0f mma_wait_peerfull=%.0f mma_total=%.0f\n",
-            fp.P, (int)train, (int)cta2, a[0] / n, a[1] / n, a[2] / n, a[3] / n);
+    double a[8] = {0}; int n = 0;
+    for (unsigned b = 0; b < cfg.gridDim.x; ++b) if (host[b * 8 + 3] > 0) { ++n; for (int k = 0; k < 8; ++k) a[k] += (double)host[b * 8 + k]; }
+    fprintf(stderr, "nb_tc prof P=%lld train=%d cta2=%d: mma_wait_aready=%.0f mma_wait_wfull=%.0f mma_wait_peerfull=%.0f mma_total=%.0f "
+            "epi_wait_acc=%.0f epi_body=%.0f epi_prologue=%.0f\n",
+            fp.P, (int)train, (int)cta2, a[0] / n, a[1] / n, a[2] / n, a[3] / n, a[4] / n, a[5] / n, a[6] / n);
   }
   return NB_OK;
 }

@@ -251,14 +251,18 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        named_bar_sync(bar_id, 128);
-        if (grp_tid == 0) {
-          const size_t off = (b == 0) ? p.w.off_dfeat : p.w.off_dh[8 - b];
-          bulk_s2g(p.ws + off + (size_t)tile * 4 * kBlobBytes, act_base, 4 * kBlobBytes);
-          bulk_commit();
-        }
-        store_pending = true;
+        named_bar_sync(bar_id, 128);                       // the whole dY tile is in shared memory
         if (b < kBwdSteps - 1) mbar_arrive(b_aready + 8 * slot);
+        {
+          // dY tile -> workspace for wgrad: coalesced copy by the epilogue threads after the MMA warp has been released
+          // (a cp.async.bulk store here competes with the weight stream for the TMA unit, see nb_mlp_tc.cu)
+          uint8_t* gdst = p.ws + ((b == 0) ? p.w.off_dfeat : p.w.off_dh[8 - b]) + (size_t)tile * 4 * kBlobBytes;
+          for (uint32_t i = (uint32_t)grp_tid; i < 4u * (kBlobBytes / 16u); i += 128u) {
+            uint4 w;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(act_base + i * 16u));
+            asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gdst + (size_t)i * 16u), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+          }
+        }
       }
     }
     if (store_pending && grp_tid == 0) bulk_wait_all0();
