@@ -210,9 +210,13 @@ __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begi
 // the peer's MMA warp forwards "my half of stage k has landed" to the leader; tcgen05.commit multicasts the
 // stage-free / accumulator-ready arrivals to both CTAs; epilogue threads of the peer arrive on the leader's
 // a_ready barrier through DSMEM (mapa + mbarrier.arrive.release.cluster).
-template <bool TRAIN, bool DBG, bool CTA2>
+// MC = true (exclusive with CTA2): clusters of two independent CTAs (each issues its own cta_group::1 MMAs) that SHARE
+// the weight stream: each CTA fetches half of every 32 KB weight stage and multicasts it into both CTAs' rings, halving
+// the L2->SM weight traffic; a stage is refilled once BOTH CTAs have retired its MMAs (commit multicast, count 2).
+template <bool TRAIN, bool DBG, bool CTA2, bool MC>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_fwd_chain_kernel(const FwdParams p) {
+  constexpr bool PAIR = CTA2 || MC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_act = sbase + kOffAct, s_aux = sbase + kOffAux, s_w = sbase + kOffW, s_bar = sbase + kOffBar;
@@ -222,20 +226,20 @@ mlp_fwd_chain_kernel(const FwdParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t NSTAGE = CTA2 ? 4u : 2u;
   constexpr uint32_t STAGE_BYTES = CTA2 ? 16384u : 32768u;
-  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
-  const bool leader = rank == 0;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = MC || rank == 0;      // MC: every CTA issues its own MMAs
 
   const long long n_tiles = (p.P + 127) / 128;
   // work units: CTA2: "pair tiles" q (tiles 2q, 2q+1 for ranks 0,1); else single tiles
-  const long long n_units = CTA2 ? (n_tiles + 1) / 2 : n_tiles;
-  const long long ncl = CTA2 ? gridDim.x / 2 : gridDim.x, cid = CTA2 ? blockIdx.x / 2 : blockIdx.x;
+  const long long n_units = PAIR ? (n_tiles + 1) / 2 : n_tiles;
+  const long long ncl = PAIR ? gridDim.x / 2 : gridDim.x, cid = PAIR ? blockIdx.x / 2 : blockIdx.x;
   auto unit_of = [&](int slot, long long it) { return (it * ncl + cid) * 2 + slot; };
   const long long max_it = (n_units + 2 * ncl - 1) / (2 * ncl);
 
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < 4; ++i) {
       mbar_init(b_wfull + 8 * i, 1);
-      mbar_init(b_wempty + 8 * i, 1);
+      mbar_init(b_wempty + 8 * i, MC ? 2 : 1);
       mbar_init(b_pfull + 8 * i, 1);
     }
     for (uint32_t i = 0; i < 2; ++i) {
@@ -247,7 +251,7 @@ mlp_fwd_chain_kernel(const FwdParams p) {
   if (warp == 1) { if (CTA2) tmem_alloc2(s_tmem, 512); else tmem_alloc(s_tmem, 512); }
   tc_fence_before();
   __syncthreads();
-  if (CTA2) cluster_sync_all();      // peer barriers are initialised before any remote arrive / multicast commit
+  if (PAIR) cluster_sync_all();      // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
@@ -259,7 +263,7 @@ mlp_fwd_chain_kernel(const FwdParams p) {
       for (long long it = 0; it < max_it; ++it) {
 #pragma unroll 1
         for (int s = 0; s < kFwdSteps; ++s) {
-          const uint32_t bytes = CTA2 ? fwd_blob_bytes(s) / 2 : fwd_blob_bytes(s);      // this CTA's share of the N rows
+          const uint32_t bytes = CTA2 ? fwd_blob_bytes(s) / 2 : fwd_blob_bytes(s);      // CTA2: this CTA's share of the N rows
           const uint8_t* src = p.wpk + fwd_w_off(s) + (CTA2 ? rank * bytes : 0u);
           for (int slot = 0; slot < 2; ++slot) {
             if (unit_of(slot, it) >= n_units) continue;
@@ -267,9 +271,17 @@ mlp_fwd_chain_kernel(const FwdParams p) {
               mbar_wait(b_wempty + 8 * stage, phase ^ 1);
               mbar_expect_tx(b_wfull + 8 * stage, bytes);
               const uint32_t q4 = bytes >> 2;
+              if (MC) {        // my half of the stage, delivered to both CTAs (the other half arrives from the peer)
+                const uint32_t hb = bytes >> 1, q2 = hb >> 1;
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                bulk_g2s(s_w + stage * STAGE_BYTES + i * q4, src + (size_t)kb * fwd_blob_bytes(s) + i * q4, q4, b_wfull + 8 * stage);
+                for (int i = 0; i < 2; ++i)
+                  bulk_g2s_mcast(s_w + stage * STAGE_BYTES + rank * hb + i * q2, src + (size_t)kb * bytes + rank * hb + i * q2, q2,
+                                 b_wfull + 8 * stage, (uint16_t)3);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  bulk_g2s(s_w + stage * STAGE_BYTES + i * q4, src + (size_t)kb * fwd_blob_bytes(s) + i * q4, q4, b_wfull + 8 * stage);
+              }
               if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
           }
@@ -313,7 +325,8 @@ mlp_fwd_chain_kernel(const FwdParams p) {
                   umma_commit_2cta(b_wempty + 8 * stage);
                   if (kb == nkb - 1) umma_commit_2cta(b_accready + 8 * slot);
                 } else {
-                  umma_commit(b_wempty + 8 * stage);                      // stage is free once these MMAs retire
+                  if (MC) umma_commit_mcast(b_wempty + 8 * stage);        // both CTAs' producers learn that I am done with it
+                  else umma_commit(b_wempty + 8 * stage);                 // stage is free once these MMAs retire
                   if (kb == nkb - 1) umma_commit(b_accready + 8 * slot);  // accumulator complete
                 }
               }
@@ -362,7 +375,7 @@ mlp_fwd_chain_kernel(const FwdParams p) {
     for (long long it = 0; it < max_it; ++it) {
       const long long unit = unit_of(slot, it);
       if (unit >= n_units) break;
-      const long long tile = CTA2 ? unit * 2 + rank : unit;
+      const long long tile = PAIR ? unit * 2 + rank : unit;
       const bool tile_ok = tile < n_tiles;                  // CTA2: the last pair may have a ghost second tile
       const long long pt = tile * 128 + r;
       const bool valid = pt < p.P;
@@ -472,7 +485,7 @@ mlp_fwd_chain_kernel(const FwdParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (CTA2) cluster_sync_all();      // nobody exits while the partner may still signal its barriers / read its smem
+  if (PAIR) cluster_sync_all();      // nobody exits while the partner may still signal its barriers / write its smem
   if (warp == 1) { if (CTA2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
@@ -592,16 +605,19 @@ int nb_tc_pack(nb_handle_t h, const nb_mlp_desc* d, const float* params, void* p
 }
 
 static int launch_fwd(nb_handle_t h, FwdParams& fp, bool train, cudaStream_t st) {
-  static bool attr_done[6] = {false, false, false, false, false, false};
+  static bool attr_done[9] = {false, false, false, false, false, false, false, false, false};
   const bool dbg = fp.dbg != nullptr;
-  static int cta2_env = -1;
-  if (cta2_env < 0) { const char* e = getenv("NB_TC_CTA2"); cta2_env = e ? atoi(e) : 0; }   // measured: pairs help only the weight stream
-  const bool cta2 = cta2_env != 0;
+  // cluster mode: 0 = independent CTAs, 1 = CTA pairs issuing cta_group::2 MMAs, 2 = independent MMAs + multicast weight ring
+  static int mode_env = -1;
+  if (mode_env < 0) { const char* e = getenv("NB_TC_CLUSTER"); mode_env = e ? atoi(e) : 2; }
+  const int mode = mode_env;
+  const bool cta2 = mode != 0;      // launched as clusters of 2
   typedef void (*kern_t)(const FwdParams);
   kern_t kern;
-  if (cta2) kern = dbg ? mlp_fwd_chain_kernel<false, true, true> : (train ? mlp_fwd_chain_kernel<true, false, true> : mlp_fwd_chain_kernel<false, false, true>);
-  else kern = dbg ? mlp_fwd_chain_kernel<false, true, false> : (train ? mlp_fwd_chain_kernel<true, false, false> : mlp_fwd_chain_kernel<false, false, false>);
-  const int ki = (dbg ? 2 : (train ? 1 : 0)) + (cta2 ? 3 : 0);
+  if (mode == 1) kern = dbg ? mlp_fwd_chain_kernel<false, true, true, false> : (train ? mlp_fwd_chain_kernel<true, false, true, false> : mlp_fwd_chain_kernel<false, false, true, false>);
+  else if (mode == 2) kern = dbg ? mlp_fwd_chain_kernel<false, true, false, true> : (train ? mlp_fwd_chain_kernel<true, false, false, true> : mlp_fwd_chain_kernel<false, false, false, true>);
+  else kern = dbg ? mlp_fwd_chain_kernel<false, true, false, false> : (train ? mlp_fwd_chain_kernel<true, false, false, false> : mlp_fwd_chain_kernel<false, false, false, false>);
+  const int ki = (dbg ? 2 : (train ? 1 : 0)) + 3 * mode;
   if (!attr_done[ki]) {
     NB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr_done[ki] = true;

@@ -14,6 +14,7 @@
 //      512 TMEM columns.  The 14 (layer, input-block) jobs run concurrently on disjoint groups of CTAs sized by
 //      their HBM traffic; bias gradients are column sums of the dY tiles taken from shared memory by spare
 //      warps; results are added to the flat fp32 gradient with red.global.add.
+#include <stdlib.h>
 #include "nb_mlp_tc.h"
 #include "nb_tc_common.cuh"
 
@@ -74,6 +75,8 @@ struct DgradParams {
   BwdWs w;
 };
 
+// MC: clusters of two CTAs sharing the W^T stream by multicast (see mlp_fwd_chain_kernel)
+template <bool MC>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_dgrad_chain_kernel(const DgradParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -82,14 +85,17 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
   const uint32_t b_wfull = s_bar, b_wempty = s_bar + 16, b_aready = s_bar + 32, b_accready = s_bar + 48, s_tmem = s_bar + 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long n_tiles = (p.P + 127) / 128;
-  const long long tile_stride = 2LL * gridDim.x;
-  auto tile_of = [&](int slot, long long it) { return 2LL * blockIdx.x + slot + it * tile_stride; };
-  const long long max_it = (n_tiles + tile_stride - 1) / tile_stride;
+  const uint32_t rank = MC ? cluster_ctarank() : 0u;
+  // MC: the two CTAs of a cluster walk "pair tiles" in lockstep (tiles 2q + rank); the last pair may hold a ghost tile
+  const long long n_units = MC ? (n_tiles + 1) / 2 : n_tiles;
+  const long long ncl = MC ? gridDim.x / 2 : gridDim.x, cid = MC ? blockIdx.x / 2 : blockIdx.x;
+  auto unit_of = [&](int slot, long long it) { return (it * ncl + cid) * 2 + slot; };
+  const long long max_it = (n_units + 2 * ncl - 1) / (2 * ncl);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(b_wfull + 8 * i, 1);
-      mbar_init(b_wempty + 8 * i, 1);
+      mbar_init(b_wempty + 8 * i, MC ? 2 : 1);
       mbar_init(b_aready + 8 * i, 128);
       mbar_init(b_accready + 8 * i, 1);
     }
@@ -98,26 +104,36 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
   if (warp == 1) tmem_alloc(s_tmem, 512);
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
 
   if (warp == 0) {
-    // weight producer: every W^T K-block once per iteration, shared by both slots; 4 concurrent bulk copies per stage
+    // ---- W^T producer: 2 x 32 KB ring, ping-pong order (slot 0's whole step, then slot 1's)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (long long it = 0; it < max_it; ++it) {
-        if (tile_of(0, it) >= n_tiles) break;
 #pragma unroll 1
         for (int b = 0; b < kBwdSteps; ++b) {
           const uint8_t* src = p.wpk + bwd_w_off(b);
-          for (int kb = 0; kb < bwd_nkb(b); ++kb) {
-            mbar_wait(b_wempty + 8 * stage, phase ^ 1);
-            mbar_expect_tx(b_wfull + 8 * stage, 32768u);
+          for (int slot = 0; slot < 2; ++slot) {
+            if (unit_of(slot, it) >= n_units) continue;
+            for (int kb = 0; kb < bwd_nkb(b); ++kb) {
+              mbar_wait(b_wempty + 8 * stage, phase ^ 1);
+              mbar_expect_tx(b_wfull + 8 * stage, 32768u);
+              if (MC) {     // my half of the stage, multicast into both CTAs' rings
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              bulk_g2s(s_w + stage * 32768u + i * 8192u, src + (size_t)kb * 32768u + i * 8192u, 8192u, b_wfull + 8 * stage);
-            stage ^= 1; if (stage == 0) phase ^= 1;
+                for (int i = 0; i < 2; ++i)
+                  bulk_g2s_mcast(s_w + stage * 32768u + rank * 16384u + i * 8192u, src + (size_t)kb * 32768u + rank * 16384u + i * 8192u,
+                                 8192u, b_wfull + 8 * stage, (uint16_t)3);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  bulk_g2s(s_w + stage * 32768u + i * 8192u, src + (size_t)kb * 32768u + i * 8192u, 8192u, b_wfull + 8 * stage);
+              }
+              stage ^= 1; if (stage == 0) phase ^= 1;
+            }
           }
         }
       }
@@ -126,34 +142,30 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
     uint32_t stage = 0, phase = 0, par_a[2] = {0, 0};
     const uint32_t idesc = umma_idesc(128, 256, 0, 0);
     for (long long it = 0; it < max_it; ++it) {
-      const bool v0 = tile_of(0, it) < n_tiles, v1 = tile_of(1, it) < n_tiles;
-      if (!v0) break;
 #pragma unroll 1
       for (int b = 0; b < kBwdSteps; ++b) {
-        mbar_wait(b_aready + 0, par_a[0]); par_a[0] ^= 1;
-        if (v1) { mbar_wait(b_aready + 8, par_a[1]); par_a[1] ^= 1; }
-        tc_fence_after();
         const int nkb = bwd_nkb(b);
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(b_wfull + 8 * stage, phase);
+        for (int slot = 0; slot < 2; ++slot) {
+          if (unit_of(slot, it) >= n_units) continue;
+          mbar_wait(b_aready + 8 * slot, par_a[slot]); par_a[slot] ^= 1;
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t b_addr = s_w + stage * 32768u;
-#pragma unroll
-            for (int slot = 0; slot < 2; ++slot) {
-              if (slot == 1 && !v1) break;
+          const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(b_wfull + 8 * stage, phase);
+            tc_fence_after();
+            if (lane == 0) {
               const uint32_t a_addr = s_act + slot * kActBytes + (uint32_t)kb * kBlobBytes;
-              const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
+              const uint32_t b_addr = s_w + stage * 32768u;
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4)
                 umma_ss(d_tmem, umma_desc(a_addr + k4 * 32u, 16, 1024), umma_desc(b_addr + k4 * 32u, 16, 1024), idesc,
                         (kb | k4) ? 1u : 0u);
+              if (MC) umma_commit_mcast(b_wempty + 8 * stage); else umma_commit(b_wempty + 8 * stage);
               if (kb == nkb - 1) umma_commit(b_accready + 8 * slot);
             }
-            umma_commit(b_wempty + 8 * stage);
+            __syncwarp();
+            stage ^= 1; if (stage == 0) phase ^= 1;
           }
-          __syncwarp();
-          stage ^= 1; if (stage == 0) phase ^= 1;
         }
       }
     }
@@ -168,9 +180,11 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
     uint32_t par_acc = 0;
     bool store_pending = false;
     for (long long it = 0; it < max_it; ++it) {
-      const long long tile = tile_of(slot, it);
-      if (tile >= n_tiles) break;
-      const long long pt = tile * 128 + r;
+      if (unit_of(slot, it) >= n_units) break;
+      const long long tile_raw = MC ? unit_of(slot, it) * 2 + rank : unit_of(slot, it);
+      const bool tile_ok = tile_raw < n_tiles;               // MC: the last pair may hold a ghost tile (computed, never stored)
+      const long long tile = tile_ok ? tile_raw : 0;
+      const long long pt = tile_raw * 128 + r;
       const bool valid = pt < p.P;
       // ---- prologue: dg = (d_rgb . Wc) * (g > 0) -> act K-blocks 0,1 ; d_raw blob -> aux ----
       float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -200,7 +214,7 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
       }
       fence_proxy_async_smem();
       named_bar_sync(bar_id, 128);
-      if (grp_tid == 0) {
+      if (grp_tid == 0 && tile_ok) {
         bulk_s2g(p.ws + p.w.off_dg + (size_t)tile * 2 * kBlobBytes, act_base, 2 * kBlobBytes);
         bulk_s2g(p.ws + p.w.off_draw + (size_t)tile * 2 * kBlobBytes, aux_base, kBlobBytes);
         bulk_s2g(p.ws + p.w.off_draw + (size_t)tile * 2 * kBlobBytes + kBlobBytes, aux_base, kBlobBytes);
@@ -253,7 +267,7 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
         tc_fence_before();
         named_bar_sync(bar_id, 128);                       // the whole dY tile is in shared memory
         if (b < kBwdSteps - 1) mbar_arrive(b_aready + 8 * slot);
-        {
+        if (tile_ok) {
           // dY tile -> workspace for wgrad: coalesced copy by the epilogue threads after the MMA warp has been released
           // (a cp.async.bulk store here competes with the weight stream for the TMA unit, see nb_mlp_tc.cu)
           uint8_t* gdst = p.ws + ((b == 0) ? p.w.off_dfeat : p.w.off_dh[8 - b]) + (size_t)tile * 4 * kBlobBytes;
@@ -269,6 +283,7 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -458,7 +473,8 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
   const long long n_tiles = S.tiles;
   static bool attr_done = false;
   if (!attr_done) {
-    NB_CUDA(h, cudaFuncSetAttribute(mlp_dgrad_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    NB_CUDA(h, cudaFuncSetAttribute(mlp_dgrad_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    NB_CUDA(h, cudaFuncSetAttribute(mlp_dgrad_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     NB_CUDA(h, cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemBytes));
     attr_done = true;
   }
@@ -470,9 +486,30 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
     dp.stash = (const uint8_t*)act_save; dp.st = S; dp.ws = (uint8_t*)ws; dp.w = W;
     NB_CUDA(h, cudaMemcpyToSymbolAsync(c_bw, (const uint8_t*)packed + nb_tc_small_offset(), sizeof(TcSmall), 0,
                                        cudaMemcpyDeviceToDevice, st));
-    long long grid = (n_tiles + 1) / 2;
-    if (grid > h->sm_count) grid = h->sm_count;
-    mlp_dgrad_chain_kernel<<<(int)grid, kThreads, kSmemBytes, st>>>(dp);
+    static int mode_env = -1;
+    if (mode_env < 0) { const char* e = getenv("NB_TC_CLUSTER"); mode_env = e ? atoi(e) : 2; }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = st;
+    if (mode_env == 2) {      // clusters of 2 CTAs sharing the weight stream by multicast
+      const long long n_pairs = (n_tiles + 1) / 2;
+      long long ncl = (n_pairs + 1) / 2;
+      if (ncl > h->sm_count / 2) ncl = h->sm_count / 2;
+      if (ncl < 1) ncl = 1;
+      cfg.gridDim = dim3((unsigned)(2 * ncl));
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      NB_CUDA(h, cudaLaunchKernelEx(&cfg, mlp_dgrad_chain_kernel<true>, dp));
+    } else {
+      long long grid = (n_tiles + 1) / 2;
+      if (grid > h->sm_count) grid = h->sm_count;
+      cfg.gridDim = dim3((unsigned)grid);
+      NB_CUDA(h, cudaLaunchKernelEx(&cfg, mlp_dgrad_chain_kernel<false>, dp));
+    }
     NB_LAUNCHED(h);
   }
   // ---- (2) wgrad jobs

@@ -88,6 +88,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// multicast variant: the bytes land at the same shared-memory offset of every CTA in `mask` of the cluster and
+// complete_tx is signalled on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
 }
@@ -165,6 +171,11 @@ __device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t adesc, ui
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// single-CTA MMAs, but the arrive is multicast to the barrier at this offset in both CTAs of the cluster
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 // arrive on the mbarrier at this shared-memory offset in BOTH CTAs of the pair once the pair's MMAs have retired
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
