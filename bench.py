@@ -222,48 +222,66 @@ def run_ours(args):
     ms_step = float(t) / args.steps
     value = N_RAYS * world / (ms_step / 1e3)
 
-    # ---- roofline of the dominant kernel: CUDA events (on the launching stream) around every MLP call of a few steps.
-    # engine.mlp_forward == exactly one launch of mlp_fwd_chain_kernel<train> (42% of the step per the ncu launch list);
-    # engine.mlp_backward == cudaMemsetAsync + mlp_dgrad_chain_kernel + mlp_wgrad_kernel.
+    # ---- roofline: CUDA events (on the launching stream) around each of the three MLP kernels during a few extra steps.
+    # engine.mlp_forward == one launch of mlp_fwd_chain_kernel<train>; the backward is issued as its two ABI stages so that
+    # mlp_dgrad_chain_kernel and mlp_wgrad_kernel are timed separately.  The DOMINANT kernel by launch-list share
+    # (profiles/*launches*.csv) is mlp_wgrad_kernel, which is HBM-bound: it is the headline `roofline`.
     of, ob = eng.mlp_forward, eng.mlp_backward
-    pend = {'fwd': [], 'bwd': []}
+    pend = {'fwd': [], 'dgrad': [], 'wgrad': []}
 
-    def timed(fn, tag):
-        def wrap(*a, **k):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = fn(*a, **k)
-            e1.record()
-            pend[tag].append((e0, e1))
-            return r
-        return wrap
-    eng.mlp_forward, eng.mlp_backward = timed(of, 'fwd'), timed(ob, 'bwd')
+    def ev_pair(tag, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        pend[tag].append((e0, e1))
+        return r
+
+    def fwd_timed(*a, **k):
+        return ev_pair('fwd', lambda: of(*a, **k))
+
+    def bwd_timed(*a, **k):
+        if args.precision != 'bf16':
+            return ev_pair('wgrad', lambda: ob(*a, **k))
+        ev_pair('dgrad', lambda: ob(*a, stage=1, **k))
+        return ev_pair('wgrad', lambda: ob(*a, stage=2, **k))
+    eng.mlp_forward, eng.mlp_backward = fwd_timed, bwd_timed
     n_prof = min(args.steps, 5)
     for i in range(n_prof):
         step(i)
     torch.cuda.synchronize()
     eng.mlp_forward, eng.mlp_backward = of, ob
-    fwd_ms = [a.elapsed_time(b) for a, b in pend['fwd']]
-    bwd_ms = [a.elapsed_time(b) for a, b in pend['bwd']]
-    mlp_ms = (sum(fwd_ms) + sum(bwd_ms)) / n_prof
+    ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in pend.items()}
+    avg = {k: (sum(v) / len(v) if v else 0.0) for k, v in ms.items()}
+    mlp_ms = sum(sum(v) for v in ms.values()) / n_prof
     peak_tf, peak_hbm, peak_src = peaks()
     pts_per_launch = N_RAYS * POINTS_PER_RAY / 2.0                       # two launches per step: 64- and 192-sample nets
-    fwd_avg_ms = sum(fwd_ms) / len(fwd_ms)
-    achieved = FLOP_PER_POINT_FWD * pts_per_launch / (fwd_avg_ms / 1e3) / 1e12
-    traffic = None
+    traffic = {}
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get('mlp_fwd_chain_kernel_train_bytes_per_launch')
+        traffic = json.load(open(tpath))
     flop_step = FLOP_PER_POINT_TRAIN * N_RAYS * POINTS_PER_RAY
-    bwd_tf = (FLOP_PER_POINT_TRAIN - FLOP_PER_POINT_FWD) * pts_per_launch / (sum(bwd_ms) / len(bwd_ms) / 1e3) / 1e12
-    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
-                'traffic': traffic, 'kernel': 'mlp_fwd_chain_kernel<train> (tcgen05 fused 8x256 MLP forward incl. PE, bf16 stash stores)',
-                'algorithmic_flop_per_launch': FLOP_PER_POINT_FWD * pts_per_launch, 'avg_launch_ms': fwd_avg_ms,
-                'launches_per_step': 2, 'peak_source': peak_src,
-                'other_kernels': {'mlp_backward (dgrad chain + wgrad)': {'achieved_tflops': bwd_tf, 'frac': bwd_tf / peak_tf,
-                                                                          'avg_call_ms': sum(bwd_ms) / len(bwd_ms)}},
-                'whole_step': {'algorithmic_flop_per_step': flop_step, 'mlp_ms_per_step': mlp_ms, 'mlp_share_of_step': mlp_ms / ms_step,
-                               'achieved_tflops': flop_step / (mlp_ms / 1e3) / 1e12, 'frac': flop_step / (mlp_ms / 1e3) / 1e12 / peak_tf}}
+    fwd_tf = FLOP_PER_POINT_FWD * pts_per_launch / (avg['fwd'] / 1e3) / 1e12
+    # wgrad: algorithmic HBM bytes = every 16 KB operand blob its 14 jobs read: 93 blobs per 128-point tile
+    WGRAD_BYTES_PER_POINT = 93 * 16384 / 128.0
+    other = {'mlp_fwd_chain_kernel<train>': {'bound': 'tensor', 'achieved': fwd_tf, 'unit': 'TFLOP/s', 'frac': fwd_tf / peak_tf,
+                                             'avg_launch_ms': avg['fwd'], 'traffic': traffic.get('mlp_fwd_chain_kernel_bytes_per_launch')}}
+    if args.precision == 'bf16':
+        wg_gbs = WGRAD_BYTES_PER_POINT * pts_per_launch / (avg['wgrad'] / 1e3) / 1e9
+        dg_tf = 1115392 * pts_per_launch / (avg['dgrad'] / 1e3) / 1e12       # dgrad: 557,696 MAC per point
+        other['mlp_dgrad_chain_kernel'] = {'bound': 'tensor', 'achieved': dg_tf, 'unit': 'TFLOP/s', 'frac': dg_tf / peak_tf,
+                                           'avg_launch_ms': avg['dgrad'], 'traffic': traffic.get('mlp_dgrad_chain_kernel_bytes_per_launch')}
+        roofline = {'bound': 'hbm', 'achieved': wg_gbs, 'peak': peak_hbm, 'unit': 'GB/s', 'frac': wg_gbs / peak_hbm,
+                    'traffic': traffic.get('mlp_wgrad_kernel_bytes_per_launch'),
+                    'kernel': 'mlp_wgrad_kernel (tcgen05 weight-gradient GEMMs, MN-major operands streamed from the activation stash)',
+                    'algorithmic_bytes_per_launch': WGRAD_BYTES_PER_POINT * pts_per_launch, 'avg_launch_ms': avg['wgrad'],
+                    'launches_per_step': 2, 'peak_source': peak_src.replace('sustained bf16', 'hbm_gbs')}
+    else:
+        roofline = dict(other.pop('mlp_fwd_chain_kernel<train>'), peak=peak_tf, kernel='sgemm_kernel chain (fp32 CUDA-core parity path)',
+                        peak_source=peak_src)
+    roofline['other_kernels'] = other
+    roofline['whole_step'] = {'algorithmic_flop_per_step': flop_step, 'mlp_ms_per_step': mlp_ms, 'mlp_share_of_step': mlp_ms / ms_step,
+                              'achieved_tflops': flop_step / (mlp_ms / 1e3) / 1e12, 'frac_of_bf16_peak': flop_step / (mlp_ms / 1e3) / 1e12 / peak_tf}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: the reference-facing call train.train(...) with HOST inputs every step

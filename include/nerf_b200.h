@@ -158,6 +158,14 @@ int nb_mlp_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, co
                     const void* act_save, const float* d_raw, float* grad, int32_t accumulate, int32_t precision,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* The same backward in two separately enqueueable stages (so a caller can time them, or start the gradient
+ * all-reduce of one network while the other still runs): stage 1 = zero grad (unless accumulate) + input-gradient
+ * chain (writes dY tiles into ws), stage 2 = weight/bias gradients from ws.  stage 1 then stage 2 == nb_mlp_backward.
+ * NB_FP32 runs entirely in stage 2. */
+int nb_mlp_backward_stage(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t P,
+                          const void* act_save, const float* d_raw, float* grad, int32_t accumulate, int32_t precision,
+                          void* ws, size_t ws_bytes, int32_t stage, void* stream);
+
 /* Diagnostic (NB_BF16): run the forward chain on rays/z and dump the raw fp32 TMEM accumulators of chain
  * step `step` (0..9; before bias/activation) to acc_out[N*S,256]; raw_out[N*S,4] as nb_mlp_forward_rays. */
 int nb_mlp_tc_probe(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t N, int32_t S,

@@ -52,6 +52,7 @@ SIGNATURES = {
     'nb_mlp_forward_emb': (C.c_int, [_p, _desc, _p, _p, _i64, _p, _i64, _p, _p, _i32, _p, _sz, _p]),
     'nb_mlp_forward_rays': (C.c_int, [_p, _desc, _p, _p, _i64, _i32, _p, _p, _p, _p, _i32, _p, _sz, _p]),
     'nb_mlp_backward': (C.c_int, [_p, _desc, _p, _p, _i64, _p, _p, _p, _i32, _i32, _p, _sz, _p]),
+    'nb_mlp_backward_stage': (C.c_int, [_p, _desc, _p, _p, _i64, _p, _p, _p, _i32, _i32, _p, _sz, _i32, _p]),
     'nb_mlp_tc_probe': (C.c_int, [_p, _desc, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p]),
     'nb_composite_forward': (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'nb_composite_backward': (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p]),

@@ -88,9 +88,26 @@ extern "C" int nb_mlp_forward_rays(nb_handle_t h, const nb_mlp_desc* d, const fl
   return fwd_common(h, d, params, packed, N * S, nullptr, 0, rays, z, S, raw_out, act_save, precision, ws, ws_bytes, stream);
 }
 
+static int bwd_common(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t P,
+                      const void* act_save, const float* d_raw, float* grad, int32_t accumulate, int32_t precision,
+                      void* ws, size_t ws_bytes, void* stream, int stages);
+
 extern "C" int nb_mlp_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t P,
                                const void* act_save, const float* d_raw, float* grad, int32_t accumulate, int32_t precision,
                                void* ws, size_t ws_bytes, void* stream) {
+  return bwd_common(h, d, params, packed, P, act_save, d_raw, grad, accumulate, precision, ws, ws_bytes, stream, 3);
+}
+
+extern "C" int nb_mlp_backward_stage(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t P,
+                                     const void* act_save, const float* d_raw, float* grad, int32_t accumulate, int32_t precision,
+                                     void* ws, size_t ws_bytes, int32_t stage, void* stream) {
+  if (stage != 1 && stage != 2) return NB_ERR_INVALID;
+  return bwd_common(h, d, params, packed, P, act_save, d_raw, grad, accumulate, precision, ws, ws_bytes, stream, stage);
+}
+
+static int bwd_common(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t P,
+                      const void* act_save, const float* d_raw, float* grad, int32_t accumulate, int32_t precision,
+                      void* ws, size_t ws_bytes, void* stream, int stages) {
   NB_ENTER(h);
   int rc = nb_desc_check(h, d);
   if (rc) return rc;
@@ -103,7 +120,8 @@ extern "C" int nb_mlp_backward(nb_handle_t h, const nb_mlp_desc* d, const float*
   if (precision == NB_BF16) {
     if (!nb_tc_supported(*d)) { NB_SET_ERR(h, "mlp bf16: topology not supported by the tcgen05 kernels"); return NB_ERR_UNSUPPORTED; }
     NB_REQUIRE(h, packed, "mlp bf16 backward: packed weights required (nb_mlp_pack)");
-    return nb_tc_backward(h, d, params, packed, P, act_save, d_raw, grad, accumulate, ws, ws_bytes, (cudaStream_t)stream);
+    return nb_tc_backward(h, d, params, packed, P, act_save, d_raw, grad, accumulate, ws, ws_bytes, (cudaStream_t)stream, stages);
   }
+  if (stages == 1) return NB_OK;     // fp32 path: the whole backward runs as stage 2
   return nb_fp32_backward(h, d, params, P, act_save, d_raw, grad, accumulate, ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -31,6 +31,7 @@ int nb_tc_pack(nb_handle_t h, const nb_mlp_desc* d, const float* params, void* p
 int nb_tc_forward(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t P, const float* x,
                   int64_t ld_x, const float* rays, const float* z, int32_t S, float* raw_out, void* act_save, void* ws,
                   size_t ws_bytes, cudaStream_t st);
+// stages: bit 0 = (zero grad unless accumulate) + dgrad chain, bit 1 = wgrad
 int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t P,
                    const void* act_save, const float* d_raw, float* grad, int accumulate, void* ws, size_t ws_bytes,
-                   cudaStream_t st);
+                   cudaStream_t st, int stages = 3);

@@ -459,7 +459,7 @@ void nb_tc_bwd_add_blobs(const NbParamLayout& L, const std::function<void(size_t
 
 int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t P,
                    const void* act_save, const float* d_raw, float* grad, int accumulate, void* ws, size_t ws_bytes,
-                   cudaStream_t st) {
+                   cudaStream_t st, int stages) {
   const NbParamLayout L = nb_param_layout(*d);
   const BwdWs W = bwd_ws_layout(P);
   if (!ws || ws_bytes < W.total) {
@@ -468,7 +468,7 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
   }
   NB_REQUIRE(h, ((uintptr_t)d_raw & 15) == 0 && ((uintptr_t)ws & 15) == 0 && ((uintptr_t)act_save & 15) == 0,
              "mlp bf16 backward: d_raw / act_save / ws must be 16-byte aligned");
-  if (!accumulate) NB_CUDA(h, cudaMemsetAsync(grad, 0, L.total * sizeof(float), st));
+  if (!accumulate && (stages & 1)) NB_CUDA(h, cudaMemsetAsync(grad, 0, L.total * sizeof(float), st));
   const TcStash S = nb_tc_stash_layout(P);
   const long long n_tiles = S.tiles;
   static bool attr_done = false;
@@ -479,7 +479,7 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
     attr_done = true;
   }
   // ---- (1) dgrad chain
-  {
+  if (stages & 1) {
     DgradParams dp;
     memset(&dp, 0, sizeof(dp));
     dp.P = P; dp.wpk = (const uint8_t*)packed + nb_tc_fwd_packed_bytes(); dp.prm = params; dp.L = L; dp.d_raw = d_raw;
@@ -513,7 +513,7 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
     NB_LAUNCHED(h);
   }
   // ---- (2) wgrad jobs
-  {
+  if (stages & 2) {
     WgradParams wp;
     memset(&wp, 0, sizeof(wp));
     wp.n_tiles = n_tiles;

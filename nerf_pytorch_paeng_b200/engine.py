@@ -201,12 +201,17 @@ class Engine:
                        _ptr(rays), _ptr(z), _ptr(raw), _ptr(act), precision, _ptr(ws), ws.numel(), self.stream)
         return raw, act
 
-    def mlp_backward(self, desc, params, packed, precision, n_pts, act, d_raw, grad, accumulate=False):
+    def mlp_backward(self, desc, params, packed, precision, n_pts, act, d_raw, grad, accumulate=False, stage=None):
+        """stage None: whole backward; 1 / 2: the two halves of nb_mlp_backward_stage (dgrad chain / wgrad)."""
         d_raw = _chk32(d_raw, 'd_raw')
         _, _, ws_b = self.mlp_bytes(desc, n_pts, precision)
         ws = self.workspace(ws_b)
-        self._call('nb_mlp_backward', C.byref(desc), _ptr(params), _ptr(packed), n_pts, _ptr(act), _ptr(d_raw), _ptr(grad),
-                   1 if accumulate else 0, precision, _ptr(ws), ws.numel(), self.stream)
+        if stage is None:
+            self._call('nb_mlp_backward', C.byref(desc), _ptr(params), _ptr(packed), n_pts, _ptr(act), _ptr(d_raw), _ptr(grad),
+                       1 if accumulate else 0, precision, _ptr(ws), ws.numel(), self.stream)
+        else:
+            self._call('nb_mlp_backward_stage', C.byref(desc), _ptr(params), _ptr(packed), n_pts, _ptr(act), _ptr(d_raw), _ptr(grad),
+                       1 if accumulate else 0, precision, _ptr(ws), ws.numel(), int(stage), self.stream)
 
     def mlp_tc_probe(self, desc, params, packed, rays, z, step):
         """Diagnostic: fp32 TMEM accumulators of chain step `step` ([P,256]) and raw [P,4]."""

@@ -220,7 +220,7 @@ def emulate_backward(p, st, d_raw, P):
     return grads
 
 
-@pytest.mark.parametrize('n,s', [(3, 50), (300, 192)])
+@pytest.mark.parametrize('n,s', [(3, 50), (5, 60), (300, 192)])   # (5,60): 3 tiles -> a ghost tile in the last CTA pair
 def test_tc_backward_kernels(setup, n, s):
     """dgrad chain + wgrad against a numpy emulation of the same bf16 data flow driven by the kernel's own
     stash (saved activations and ReLU masks): isolates the backward kernels from forward rounding."""
