@@ -59,7 +59,8 @@ constexpr uint32_t kOffAux = 2 * kActBytes;
 constexpr uint32_t kOffW = kOffAux + 2 * kBlobBytes;
 constexpr uint32_t kOffBar = kOffW + 2 * 32768;
 constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;
-constexpr int kThreads = 320;
+constexpr int kThreads = 576;      // warp 0 producer, warp 1 MMA, 8 epilogue warps per slot (two per TMEM lane quarter: column halves)
+constexpr int kEpi = 256;
 
 __constant__ TcSmall c_bw;   // small fp32 parameters (sigma / rgb head weights) of the network being differentiated
 
@@ -96,7 +97,7 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(b_wfull + 8 * i, 1);
       mbar_init(b_wempty + 8 * i, MC ? 2 : 1);
-      mbar_init(b_aready + 8 * i, 128);
+      mbar_init(b_aready + 8 * i, kEpi);
       mbar_init(b_accready + 8 * i, 1);
     }
     fence_barrier_init();
@@ -170,12 +171,13 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
       }
     }
   } else {
-    const int slot = (warp - 2) >> 2;
+    const int slot = (warp - 2) >> 3;
+    const int half = ((warp - 2) >> 2) & 1;              // column half of the tile this warp handles
     const uint32_t q = (uint32_t)warp & 3u;
     const uint32_t r = q * 32u + (uint32_t)lane;
     const uint32_t act_base = s_act + slot * kActBytes, aux_base = s_aux + slot * kBlobBytes;
     const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + (uint32_t)slot * 256u;
-    const int grp_tid = threadIdx.x - (64 + slot * 128);
+    const int grp_tid = threadIdx.x - (64 + slot * kEpi);
     const int bar_id = 1 + slot;
     uint32_t par_acc = 0;
     bool store_pending = false;
@@ -192,9 +194,9 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
       const uint32_t* mrow = reinterpret_cast<const uint32_t*>(p.stash + p.st.off_mask) + ((size_t)tile * 9 * 128 + r) * 8;
       const uint4 gm = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)8 * 128 * 8));       // mask of g (128 columns)
       const uint32_t gmw[4] = {gm.x, gm.y, gm.z, gm.w};
-      if (store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, 128); store_pending = false; }
+      if (store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, kEpi); store_pending = false; }
 #pragma unroll 1
-      for (int c = 0; c < 16; ++c) {
+      for (int c = half * 8; c < half * 8 + 8; ++c) {      // dg columns of this half (one K-block)
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -207,13 +209,13 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
                      pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
       }
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = half * 4; c < half * 4 + 4; ++c) {
         uint32_t w0 = 0, w1 = 0;
         if (c == 0) { w0 = pack_bf16(dr.x, dr.y); w1 = pack_bf16(dr.z, dr.w); }
         st_shared_v4(aux_base + sw128_chunk(r, (uint32_t)c), w0, w1, 0u, 0u);
       }
       fence_proxy_async_smem();
-      named_bar_sync(bar_id, 128);
+      named_bar_sync(bar_id, kEpi);
       if (grp_tid == 0 && tile_ok) {
         bulk_s2g(p.ws + p.w.off_dg + (size_t)tile * 2 * kBlobBytes, act_base, 2 * kBlobBytes);
         bulk_s2g(p.ws + p.w.off_draw + (size_t)tile * 2 * kBlobBytes, aux_base, kBlobBytes);
@@ -234,10 +236,10 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
         }
         mbar_wait(b_accready + 8 * slot, par_acc); par_acc ^= 1;
         tc_fence_after();
-        if (store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, 128); store_pending = false; }
+        if (store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, kEpi); store_pending = false; }
         // rolled on purpose: one 32-column body stays resident in the instruction cache (see nb_mlp_tc.cu)
 #pragma unroll 1
-        for (int c32 = 0; c32 < 8; ++c32) {
+        for (int c32 = half * 4; c32 < half * 4 + 4; ++c32) {
           float v[32];
           tmem_ld32(t_addr + (uint32_t)c32 * 32u, v);
           tmem_ld_wait();
@@ -265,13 +267,13 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        named_bar_sync(bar_id, 128);                       // the whole dY tile is in shared memory
+        named_bar_sync(bar_id, kEpi);                       // the whole dY tile is in shared memory
         if (b < kBwdSteps - 1) mbar_arrive(b_aready + 8 * slot);
         if (tile_ok) {
           // dY tile -> workspace for wgrad: coalesced copy by the epilogue threads after the MMA warp has been released
           // (a cp.async.bulk store here competes with the weight stream for the TMA unit, see nb_mlp_tc.cu)
           uint8_t* gdst = p.ws + ((b == 0) ? p.w.off_dfeat : p.w.off_dh[8 - b]) + (size_t)tile * 4 * kBlobBytes;
-          for (uint32_t i = (uint32_t)grp_tid; i < 4u * (kBlobBytes / 16u); i += 128u) {
+          for (uint32_t i = (uint32_t)grp_tid; i < 4u * (kBlobBytes / 16u); i += (uint32_t)kEpi) {
             uint4 w;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(act_base + i * 16u));
             asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gdst + (size_t)i * 16u), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
