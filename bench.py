@@ -154,7 +154,7 @@ def run_reference(args):
                              'sample': f'{n}-ray train step (render+grads+Adam) of oracle/nerf_oracle.py, numpy/BLAS threads={cores}'},
             'e2e': {'value': val, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -354,10 +354,29 @@ def run_ours(args):
                        'loss': float(loss.sum())},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'render': render, 'gpu_launches': int(launches), 'clocks': clocks,
             'gpu_launches_per_step': launches / args.steps}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def _claim_stdout():
+    """Keep stdout for the single JSON line: everything else this process (or NCCL, which prints its version banner
+    on stdout) writes to fd 1 is sent to stderr; returns a file object on the original stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+    return real
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + '\n')
+    _REAL_STDOUT.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
