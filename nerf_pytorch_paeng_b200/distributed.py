@@ -39,6 +39,10 @@ class DistContext:
         for w in works:
             w.wait()
 
+    def allreduce_grad_async(self, net):
+        """Start the sum all-reduce of one network's flat gradient; returns the work handle (wait() before the optimiser)."""
+        return dist.all_reduce(net.bind_flat_grad(), op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
     def gather_rows(self, local, n_total):
         """All-gather variable-length row bands (dim 0) into the full [n_total, ...] tensor."""
         sizes = [shard_range(n_total, r, self.world_size) for r in range(self.world_size)]

@@ -56,7 +56,7 @@ class FlatAdam:
                 self.state[id(n)] = tuple(t.clone() for t in st)
 
 
-def render_losses_and_grads(model, rays, target, opts, n_global=None, want_grads=True, loss_buf=None):
+def render_losses_and_grads(model, rays, target, opts, n_global=None, want_grads=True, loss_buf=None, on_net_done=None):
     """Forward coarse+fine, loss, and (optionally) parameter gradients into the flat buffers.
 
     rays [N,6] (already NDC-warped for llff), target [N,3].  n_global: total rays over all ranks
@@ -90,6 +90,8 @@ def render_losses_and_grads(model, rays, target, opts, n_global=None, want_grads
             grad = net.bind_flat_grad()
             eng.mlp_backward(net.desc, flat, net.packed_weights(), net.precision, n * z.shape[1], act, d_raw.view(-1, 4), grad)
             del act
+            if on_net_done is not None:
+                on_net_done(net)          # e.g. start this network's gradient all-reduce while the other network runs
         z_prev, w_prev = z, w
     return out
 
@@ -97,10 +99,17 @@ def render_losses_and_grads(model, rays, target, opts, n_global=None, want_grads
 def train_step(model, optimizer, rays, target, opts, dist_ctx=None):
     """One optimisation step on a ray batch; returns the device tensor [loss_c, loss_f] (global means)."""
     n_global = rays.shape[0] * (dist_ctx.world_size if dist_ctx is not None else 1)
-    out = render_losses_and_grads(model, rays, target, opts, n_global=n_global)
+    works = []
+    hook = None
     if dist_ctx is not None:
-        dist_ctx.allreduce_grads(model)
+        # the two networks' gradients are independent (nerf_process.py:66 detaches the fine samples): the coarse
+        # net's all-reduce is launched as soon as its backward is enqueued and overlaps the whole fine pass
+        hook = lambda net: works.append(dist_ctx.allreduce_grad_async(net))
+    out = render_losses_and_grads(model, rays, target, opts, n_global=n_global, on_net_done=hook)
+    if dist_ctx is not None:
         dist_ctx.allreduce_(out['loss_buf'])
+        for w in works:
+            w.wait()
     optimizer.step()
     return out['loss_buf']
 

@@ -202,3 +202,87 @@ def test_two_gpu_equals_one_gpu(tmp_path):
             assert rel <= 1e-4, (key, rel)        # fp32 atomics order only
         assert float((d['loss'] - out['loss_buf'].cpu()).abs().max()) <= 1e-6
         assert float((d['rgb_f'] - out['rgb_f'].cpu()).abs().max()) <= 1e-5
+
+
+def test_train_entry_global_batch():
+    """train.py:25-32: the global-batch path (device-resident shuffled [N,3,3] ray/rgb table + GetterRayBatchIdx cursor)."""
+    from nerf_pytorch_paeng_b200 import rays as rays_mod, train as train_mod, trainer
+    from nerf_pytorch_paeng_b200.model import NeRF, get_positional_encoder
+    from nerf_pytorch_paeng_b200.utils import GetterRayBatchIdx
+    g = load_golden('raygen.npz')
+    H, W = 30, 40
+    K = np.array([[50., 0, W / 2], [0, 50., H / 2], [0, 0, 1.]])
+    poses = g['all_poses'][:2].astype(np.float32)
+    table = []
+    for pose in poses:                                   # main.py:95-101
+        o, d = rays_mod.get_rays_np(H, W, K, pose)
+        table.append(np.stack([o, d, np.full_like(d, 0.3)], 0))
+    rays_rgb = np.transpose(np.stack(table, 0), [0, 2, 3, 1, 4]).reshape(-1, 3, 3).astype(np.float32)
+    np.random.seed(0)
+    np.random.shuffle(rays_rgb)
+    cursor = GetterRayBatchIdx(torch.from_numpy(rays_rgb).cuda())
+    torch.manual_seed(0)
+    net = NeRF(8, 256, 63, 27, [4], gt_camera_param=(K, poses)).cuda().set_precision('bf16')
+    opts = make_opts(N_rays=600, global_batch=True)
+    opt = trainer.FlatAdam(net, lr=2e-3)
+    posenc = [get_positional_encoder(10)[0], get_positional_encoder(4)[0]]
+    losses = [float(train_mod.train(i, [0, 1], None, (K, poses), (H, W), net, torch.nn.MSELoss(), posenc, opt, cursor, None, opts))
+              for i in range(1, 11)]
+    assert cursor.epoch >= 1                             # 2400 rays / 600 per step: wrapped and reshuffled (utils.py:54-58)
+    assert np.isfinite(losses).all() and np.mean(losses[-3:]) < 0.7 * np.mean(losses[:3]), losses
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] at full size (4096 rays, 64+128) through size-independent properties of the domain."""
+    from nerf_pytorch_paeng_b200 import nerf_process, trainer
+    from nerf_pytorch_paeng_b200.engine import get_engine
+    from nerf_pytorch_paeng_b200.model import NeRF
+    eng = get_engine(torch.device('cuda', 0))
+    torch.manual_seed(0)
+    net = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).cuda().set_precision('bf16')
+    with torch.no_grad():
+        net.model_coarse.linear_density.weight.mul_(30.)
+        net.model_fine.linear_density.weight.mul_(30.)
+    n = 4096
+    K = np.array([[1111.111, 0, 400.], [0, 1111.111, 400.], [0, 0, 1.]])
+    g = load_golden('raygen.npz')
+    pix = eng.select_pixels(n, 800, 800, seed=3)
+    o, d = eng.raygen(800, 800, K, cu(g['pose8']), pix_idx=pix)
+    rays = torch.cat((o, d), -1)
+    opts = make_opts(N_rays=n, seed=11)
+    z_c = nerf_process._coarse_z(rays, opts)
+    m = net.model_coarse
+    raw, _ = eng.mlp_forward(m.desc, m.flat_params(), m.packed_weights(), m.precision, rays=rays, z=z_c)
+    rgb, disp, acc, w, depth = eng.composite_forward(raw.view(n, 64, 4), z_c, d)
+    # compositing: weights are a sub-probability vector; rgb = sum w*sigmoid(c) + (1 - acc); depth inside [near, far]
+    assert float(w.min()) >= 0. and float(acc.max()) <= 1. + 1e-5
+    recon = (w[..., None] * torch.sigmoid(raw.view(n, 64, 4)[..., :3])).sum(1) + (1. - acc[:, None])
+    assert float((recon - rgb).abs().max()) <= 1e-5
+    assert float(rgb.min()) >= -1e-6 and float(rgb.max()) <= 1. + 1e-5
+    assert float((depth - acc * 6.0).max()) <= 1e-3 and float((depth - acc * 2.0).min()) >= -1e-3
+    assert float(disp.min()) >= 0. and float(disp.max()) <= 5.
+    # hierarchical sampling: sorted, 192 per ray, contains every coarse depth, new samples inside the coarse span
+    z_f = nerf_process._fine_z(rays, opts, z_c, w)
+    assert z_f.shape == (n, 192) and bool((z_f[:, 1:] >= z_f[:, :-1]).all())
+    both = torch.sort(torch.cat([z_f, z_c], -1), -1)[0]
+    assert int((both[:, 1:] == both[:, :-1]).sum(-1).min()) >= 64           # every coarse value appears again
+    assert float(z_f.min()) >= float(z_c.min()) - 1e-6 and float(z_f.max()) <= float(z_c.max()) + 1e-6
+    # MLP rows are independent: permuting the rays permutes raw bit-exactly (tile / slot / cluster placement invariance)
+    perm = torch.randperm(n, device='cuda')
+    raw_p, _ = eng.mlp_forward(m.desc, m.flat_params(), m.packed_weights(), m.precision, rays=rays[perm].contiguous(), z=z_c[perm].contiguous())
+    assert torch.equal(raw_p.view(n, 64, 4), raw.view(n, 64, 4)[perm])
+    # a ragged prefix gives the same rows as the full batch
+    raw_r, _ = eng.mlp_forward(m.desc, m.flat_params(), m.packed_weights(), m.precision, rays=rays[:1001].contiguous(), z=z_c[:1001].contiguous())
+    assert torch.equal(raw_r, raw[:1001 * 64])
+    # backward is linear in the upstream gradient, and the step is deterministic up to fp32 atomic order
+    target = torch.rand(n, 3, device='cuda')
+    nerf_process._counter[0] = 0
+    trainer.render_losses_and_grads(net, rays, target, opts)
+    g1 = net.model_fine.flat_grad.clone()
+    nerf_process._counter[0] = 0
+    trainer.render_losses_and_grads(net, rays, target, opts)
+    g2 = net.model_fine.flat_grad.clone()
+    assert float((g1 - g2).norm() / g1.norm()) <= 1e-5
+    nerf_process._counter[0] = 0
+    trainer.render_losses_and_grads(net, rays, target, opts, n_global=n // 2)    # loss scaled x2 -> gradient x2
+    assert float((net.model_fine.flat_grad - 2 * g1).norm() / g1.norm()) <= 1e-3
