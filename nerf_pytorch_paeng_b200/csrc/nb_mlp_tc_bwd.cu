@@ -551,18 +551,20 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
     add(w8 + W.off_draw, 2, 0, 2, stash + S.off_g, 2, 0, 2, grad + L.wc, 128, 0, 3, 128, grad + L.bc);          // dWc, dbc
     add(w8 + W.off_draw, 2, 0, 2, stash + S.off_h[7], 4, 0, 4, grad + L.ws, 256, 3, 4, 256, grad + L.bs);       // dWsigma, dbsigma
     wp.n_jobs = nj;
-    // distribute the CTAs over jobs proportionally to their traffic
-    int total_w = 0;
-    for (int j = 0; j < nj; ++j) total_w += weight[j];
+    // distribute the CTAs over the jobs so that the largest (traffic / CTAs) ratio is as small as possible: start from one CTA
+    // per job and hand out the rest greedily to the currently most loaded job (the kernel ends with its slowest job)
     int n_cta = h->sm_count;
-    int given = 0;
-    for (int j = 0; j < nj; ++j) {
-      int c = (int)((long long)weight[j] * n_cta / total_w);
-      if (c < 1) c = 1;
-      wp.job[j].cta_count = c;
-      given += c;
+    if (n_cta < nj) n_cta = nj;
+    for (int j = 0; j < nj; ++j) wp.job[j].cta_count = 1;
+    for (int given = nj; given < n_cta; ++given) {
+      int worst = 0;
+      double worst_load = -1.0;
+      for (int j = 0; j < nj; ++j) {
+        const double load = (double)weight[j] / wp.job[j].cta_count;
+        if (load > worst_load) { worst_load = load; worst = j; }
+      }
+      wp.job[worst].cta_count++;
     }
-    for (int j = 0; given < n_cta; j = (j + 1) % nj) { wp.job[j].cta_count++; given++; }
     int begin = 0;
     for (int j = 0; j < nj; ++j) { wp.job[j].cta_begin = begin; begin += wp.job[j].cta_count; }
     mlp_wgrad_kernel<<<begin, kWgThreads, kWgSmemBytes, st>>>(wp);
