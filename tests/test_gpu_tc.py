@@ -1,6 +1,8 @@
 """GPU tests of the tcgen05 (NB_BF16) MLP path: step-by-step against a numpy emulation of the same
 bf16 data flow, and end to end against the fp32 path / oracle (north_star: >= 50 dB PSNR, gradients
 within 1e-2 relative)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -328,3 +330,15 @@ def test_tc_train_step_matches_fp32(setup):
     # north_star: bf16 MLP path gradients within 1e-2 relative (whole gradient vector of each network)
     assert np.linalg.norm(gc16 - gc32) / np.linalg.norm(gc32) <= 1e-2
     assert np.linalg.norm(gf16 - gf32) / np.linalg.norm(gf32) <= 1e-2
+
+
+@pytest.mark.parametrize('mode', ['0', '1', '2'])
+def test_tc_cluster_modes(mode):
+    """Every cluster mode of the chain kernels (0: independent CTAs, 1: cta_group::2 pairs for the forward, 2: multicast
+    weight ring -- the default) gives the same results; the mode is fixed per process, hence the subprocess."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    env = dict(os.environ, NB_TC_CLUSTER=mode)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'tc_mode_check.py')], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'OK' in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
