@@ -20,6 +20,14 @@ from .rays import make_o_d_selected
 from .utils import mse2psnr
 
 _cache = {}
+_streams = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _streams:
+        _streams[key] = torch.cuda.Stream(device=device)
+    return _streams[key]
 
 
 def _device_copy(arr, device, key):
@@ -74,13 +82,25 @@ def train(idx, i_train, images, gt_cam_param, hw, model, criterion, posenc, opti
             pix = torch.from_numpy(select_pixels(idx, img_h, img_w, opts)).to(device, non_blocking=True)
         img = images[i_img]
         img = img if isinstance(img, torch.Tensor) else torch.from_numpy(img)
-        img = img.to(device=device, dtype=torch.float32, non_blocking=True)      # H2D of the target image
+        # H2D of the target image (train.py:37-38) on a side stream: it is only needed at the first loss, so the copy
+        # overlaps ray generation and the coarse forward
+        side = _side_stream(device)
+        with torch.cuda.stream(side):
+            img_dev = img.to(device=device, dtype=torch.float32, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(side)
         rays_o, rays_d = make_o_d_selected(img_w, img_h, gt_intrinsic, pose, pix, ndc=llff, near=1.)
         from .engine import get_engine
-        target = get_engine(device).gather_rows(img.reshape(-1, 3), pix)
+
+        def target():
+            torch.cuda.current_stream(device).wait_event(copied)
+            img_dev.record_stream(torch.cuda.current_stream(device))
+            return get_engine(device).gather_rows(img_dev.reshape(-1, 3), pix)
     rays = torch.cat((rays_o, rays_d), dim=-1)
 
     fused = isinstance(criterion, torch.nn.MSELoss) or criterion is None
+    if not fused and callable(target):
+        target = target()
     if fused:
         for net in (model.model_coarse, model.model_fine):
             net.bind_flat_grad()

@@ -56,43 +56,71 @@ class FlatAdam:
                 self.state[id(n)] = tuple(t.clone() for t in st)
 
 
+MAX_POINTS_PER_PASS = 6 * 1024 * 1024      # activation stash + dY workspace ~ 10 KB/point (bf16) -> ~60 GB per pass at most
+
+
 def render_losses_and_grads(model, rays, target, opts, n_global=None, want_grads=True, loss_buf=None, on_net_done=None):
     """Forward coarse+fine, loss, and (optionally) parameter gradients into the flat buffers.
 
-    rays [N,6] (already NDC-warped for llff), target [N,3].  n_global: total rays over all ranks
-    (the MSE mean is over the GLOBAL batch so that summed rank gradients equal the single-GPU
-    gradient).  Returns dict(rgb_c, rgb_f, disp_c, disp_f, loss_buf[2] device tensor).
+    rays [N,6] (already NDC-warped for llff), target [N,3] -- or a callable returning it, evaluated right before the first
+    loss so that e.g. a host->device copy of the target image can overlap the coarse forward.  n_global: total rays over all
+    ranks (the MSE mean is over the GLOBAL batch so that summed rank gradients equal the single-GPU gradient).
+    Batches whose point count would not fit the activation stash (BASELINE config 5: up to 64k rays x 256+512 samples) are
+    processed in ray chunks with gradient accumulation.  Returns dict(rgb_c, rgb_f, disp_c, disp_f, loss_buf[2] device tensor).
     """
     eng = get_engine(rays.device)
     n = rays.shape[0]
     n_global = n if n_global is None else n_global
     rays = rays.contiguous()
-    rays_d = rays[:, 3:].contiguous()
     scale = 2.0 / (3.0 * n_global)
     if loss_buf is None:
         loss_buf = torch.zeros(2, device=rays.device)
     out = {'loss_buf': loss_buf}
-    z_prev = w_prev = None
-    for i, fine in enumerate((False, True)):
-        if fine and opts.N_samples_f <= 0:
-            break
-        net = model.model_fine if fine else model.model_coarse
-        flat = net.flat_params()
-        z = NP._fine_z(rays, opts, z_prev, w_prev) if fine else NP._coarse_z(rays, opts)
-        raw, act = eng.mlp_forward(net.desc, flat, net.packed_weights(), net.precision, rays=rays, z=z, save=want_grads)
-        raw3 = raw.view(n, z.shape[1], 4)
-        rgb, disp, acc, w, depth = eng.composite_forward(raw3, z, rays_d, want_all=not fine)
-        tag = 'f' if fine else 'c'
-        out['rgb_' + tag], out['disp_' + tag] = rgb, disp
-        d_rgb = eng.mse_grad(rgb, target, scale, 1.0 / (3.0 * n_global), loss_buf[i:i + 1], want_grad=want_grads)
-        if want_grads:
-            d_raw = eng.composite_backward(raw3, z, rays_d, d_rgb)
-            grad = net.bind_flat_grad()
-            eng.mlp_backward(net.desc, flat, net.packed_weights(), net.precision, n * z.shape[1], act, d_raw.view(-1, 4), grad)
-            del act
-            if on_net_done is not None:
-                on_net_done(net)          # e.g. start this network's gradient all-reduce while the other network runs
-        z_prev, w_prev = z, w
+    s_max = opts.N_samples_c + max(opts.N_samples_f, 0)
+    max_pts = int(getattr(opts, 'max_points_per_pass', MAX_POINTS_PER_PASS))
+    rays_per_pass = n if (not want_grads or n * s_max <= max_pts) else max(128, (max_pts // s_max) // 128 * 128)
+    tgt = None
+    rng = getattr(opts, 'rng', None)
+    parts = {k: [] for k in ('rgb_c', 'disp_c', 'rgb_f', 'disp_f')}
+    nets_done = [False, False]
+    for r0 in range(0, n, rays_per_pass):
+        r1 = min(n, r0 + rays_per_pass)
+        rays_k = rays if (r0 == 0 and r1 == n) else rays[r0:r1].contiguous()
+        rays_d = rays_k[:, 3:].contiguous()
+        if rng is not None and not (r0 == 0 and r1 == n):
+            opts.rng = {k: (v[r0:r1] if v.dim() == 2 else v) for k, v in rng.items()}
+        nk = r1 - r0
+        z_prev = w_prev = None
+        for i, fine in enumerate((False, True)):
+            if fine and opts.N_samples_f <= 0:
+                break
+            net = model.model_fine if fine else model.model_coarse
+            flat = net.flat_params()
+            z = NP._fine_z(rays_k, opts, z_prev, w_prev) if fine else NP._coarse_z(rays_k, opts)
+            raw, act = eng.mlp_forward(net.desc, flat, net.packed_weights(), net.precision, rays=rays_k, z=z, save=want_grads)
+            raw3 = raw.view(nk, z.shape[1], 4)
+            rgb, disp, acc, w, depth = eng.composite_forward(raw3, z, rays_d, want_all=not fine)
+            tag = 'f' if fine else 'c'
+            parts['rgb_' + tag].append(rgb)
+            parts['disp_' + tag].append(disp)
+            if tgt is None:
+                tgt = target() if callable(target) else target
+            tgt_k = tgt if (r0 == 0 and r1 == n) else tgt[r0:r1]
+            d_rgb = eng.mse_grad(rgb, tgt_k, scale, 1.0 / (3.0 * n_global), loss_buf[i:i + 1], want_grad=want_grads)
+            if want_grads:
+                d_raw = eng.composite_backward(raw3, z, rays_d, d_rgb)
+                grad = net.bind_flat_grad()
+                eng.mlp_backward(net.desc, flat, net.packed_weights(), net.precision, nk * z.shape[1], act, d_raw.view(-1, 4), grad,
+                                 accumulate=r0 > 0)
+                del act
+                if on_net_done is not None and r1 == n:
+                    on_net_done(net)      # e.g. start this network's gradient all-reduce while the other network runs
+            z_prev, w_prev = z, w
+    if rng is not None:
+        opts.rng = rng
+    for k, v in parts.items():
+        if v:
+            out[k] = v[0] if len(v) == 1 else torch.cat(v, 0)
     return out
 
 

@@ -286,3 +286,29 @@ def test_full_size_properties():
     nerf_process._counter[0] = 0
     trainer.render_losses_and_grads(net, rays, target, opts, n_global=n // 2)    # loss scaled x2 -> gradient x2
     assert float((net.model_fine.flat_grad - 2 * g1).norm() / g1.norm()) <= 1e-3
+
+
+def test_chunked_gradient_accumulation():
+    """Batches too large for one activation stash are processed in ray chunks with gradient accumulation
+    (BASELINE config 5 sizes); the result equals the single-pass step."""
+    from nerf_pytorch_paeng_b200 import trainer
+    from nerf_pytorch_paeng_b200.model import NeRF
+    g = load_golden('raygen.npz')
+    n = 900
+    rs = np.random.RandomState(1)
+    rays = cu(np.concatenate([np.tile(g['rays_o8'][:1], (n, 1)), g['rays_d8'][:n]], -1))
+    target = cu(rs.rand(n, 3))
+    rng = {'t_rand': cu(rs.rand(n, 64)), 'u': cu(rs.rand(n, 128))}
+    torch.manual_seed(0)
+    net = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).cuda().set_precision('fp32')
+    res = []
+    for max_pts in (10 ** 9, 256 * 192):          # single pass vs chunks of 256 rays (last chunk ragged: 132 rays)
+        opts = make_opts(rng=dict(rng), max_points_per_pass=max_pts)
+        out = trainer.render_losses_and_grads(net, rays, target, opts)
+        torch.cuda.synchronize()
+        res.append((out['loss_buf'].clone(), out['rgb_f'].clone(), net.model_coarse.flat_grad.clone(), net.model_fine.flat_grad.clone()))
+    a, b = res
+    assert float((a[0] - b[0]).abs().max()) <= 1e-6
+    assert float((a[1] - b[1]).abs().max()) <= 1e-5 and b[1].shape == (n, 3)
+    assert float((a[2] - b[2]).norm() / a[2].norm()) <= 1e-4
+    assert float((a[3] - b[3]).norm() / a[3].norm()) <= 1e-4
