@@ -193,7 +193,7 @@ __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begi
           w0 = pack_bf16_relu(v[j * 8 + 0], v[j * 8 + 1]); w1 = pack_bf16_relu(v[j * 8 + 2], v[j * 8 + 3]);
           w2 = pack_bf16_relu(v[j * 8 + 4], v[j * 8 + 5]); w3 = pack_bf16_relu(v[j * 8 + 6], v[j * 8 + 7]);
         }
-        st_shared_v4(row_addr + ((c ^ (r & 7u)) << 4), w0, w1, w2, w3);
+        if (!(p.abl & 4)) st_shared_v4(row_addr + ((c ^ (r & 7u)) << 4), w0, w1, w2, w3);
         // training: the same 16 bytes go straight to the stash blob (same swizzled image).  Direct stores keep the
         // TMA unit and the shared-memory read port free for the weight stream and the MMA operands.
         if (TRAIN && kDirectStash && gdst != nullptr)
@@ -269,6 +269,7 @@ mlp_fwd_chain_kernel(const FwdParams p) {
             if (unit_of(slot, it) >= n_units) continue;
             for (int kb = 0; kb < fwd_nkb(s); ++kb) {
               mbar_wait(b_wempty + 8 * stage, phase ^ 1);
+              if (p.abl & 8) { mbar_arrive(b_wfull + 8 * stage); if (++stage == NSTAGE) { stage = 0; phase ^= 1; } continue; }
               mbar_expect_tx(b_wfull + 8 * stage, bytes);
               const uint32_t q4 = bytes >> 2;
               if (MC) {        // my half of the stage, delivered to both CTAs (the other half arrives from the peer)
@@ -677,7 +678,7 @@ int nb_tc_forward(nb_handle_t h, const nb_mlp_desc* d, const float* params, cons
   fp.wpk = (const uint8_t*)packed; fp.prm = params; fp.L = nb_param_layout(*d); fp.raw = raw_out;
   fp.stash = (uint8_t*)act_save; fp.st = nb_tc_stash_layout(P);
   fp.dbg = nullptr; fp.dbg_step = -1;
-  fp.abl = 0;
+  { static int ab = -1; if (ab < 0) { const char* e = getenv("NB_TC_ABLATE"); ab = e ? atoi(e) : 0; } fp.abl = ab; }   // timing experiments only
   return launch_fwd(h, fp, act_save != nullptr, st);
 }
 
