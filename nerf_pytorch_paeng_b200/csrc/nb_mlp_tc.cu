@@ -21,6 +21,7 @@
 // In training the bf16 A tiles (layer inputs) are additionally bulk-stored to HBM as 16 KB swizzled blobs
 // which the backward kernels (nb_mlp_tc_bwd.cu) consume directly as UMMA operands.
 #include <stdlib.h>
+#include <cuda.h>
 #include "nb_mlp.h"
 #include "nb_tc_common.cuh"
 #include "nb_mlp_tc.h"
@@ -66,6 +67,7 @@ constexpr int kBarEpi0 = 1;
 __constant__ TcSmall c_fw;   // small fp32 parameters of the network being run (see nb_mlp_tc.h)   // named barrier ids of the two epilogue groups
 
 struct FwdParams {
+  CUtensorMap tmap_w;     // pair mode only: packed forward blobs viewed as [rows, 64] bf16, box = 64 rows (8 KB), no swizzle (pre-swizzled images)
   const float* rays;      // [N,6]
   const float* z;         // [N,S]
   const float* x_emb;     // optional materialised embedding [P, ld_x] (forward_emb entry) or nullptr
@@ -215,7 +217,7 @@ __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begi
 // the L2->SM weight traffic; a stage is refilled once BOTH CTAs have retired its MMAs (commit multicast, count 2).
 template <bool TRAIN, bool DBG, bool CTA2, bool MC>
 __global__ void __launch_bounds__(kThreads, 1)
-mlp_fwd_chain_kernel(const FwdParams p) {
+mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
   constexpr bool PAIR = CTA2 || MC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -270,6 +272,16 @@ mlp_fwd_chain_kernel(const FwdParams p) {
             for (int kb = 0; kb < fwd_nkb(s); ++kb) {
               mbar_wait(b_wempty + 8 * stage, phase ^ 1);
               if (p.abl & 8) { mbar_arrive(b_wfull + 8 * stage); if (++stage == NSTAGE) { stage = 0; phase ^= 1; } continue; }
+              if (CTA2) {
+                // both CTAs' halves complete_tx on the LEADER's barrier (cta_group::2 tensor loads): no forwarding hop
+                if (rank == 0) mbar_expect_tx(b_wfull + 8 * stage, 2 * bytes);
+                const uint32_t lbar = (b_wfull + 8 * stage) & 0xFEFFFFFFu;
+                const int row0 = (int)((fwd_w_off(s) + (uint32_t)kb * fwd_blob_bytes(s) + rank * bytes) >> 7);
+                for (uint32_t i = 0; i < bytes; i += 8192u)
+                  tma_load_2d_pair(s_w + stage * STAGE_BYTES + i, &p.tmap_w, 0, row0 + (int)(i >> 7), lbar);
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                continue;
+              }
               mbar_expect_tx(b_wfull + 8 * stage, bytes);
               const uint32_t q4 = bytes >> 2;
               if (MC) {        // my half of the stage, delivered to both CTAs (the other half arrives from the peer)
@@ -310,7 +322,7 @@ mlp_fwd_chain_kernel(const FwdParams p) {
             const uint32_t d_tmem = tmem_base + (uint32_t)slot * 256u;
             for (int kb = 0; kb < nkb; ++kb) {
               { const long long t0 = clock64(); mbar_wait(b_wfull + 8 * stage, phase); const long long t1 = clock64(); pw += t1 - t0;
-                if (CTA2) { mbar_wait_cluster(b_pfull + 8 * stage, phase); pp += clock64() - t1; } }
+                (void)t1; }
               tc_fence_after();
               if (lane == 0) {
                 const int src = fwd_a_src(s, kb);
@@ -342,21 +354,7 @@ mlp_fwd_chain_kernel(const FwdParams p) {
         o[0] = pa; o[1] = pw; o[2] = pp; o[3] = clock64() - tstart;
       }
     } else {
-      // ============================== peer: forward "my half landed" to the leader ==============================
-      if (lane == 0) {
-        for (long long it = 0; it < max_it; ++it) {
-#pragma unroll 1
-          for (int s = 0; s < kFwdSteps; ++s)
-            for (int slot = 0; slot < 2; ++slot) {
-              if (unit_of(slot, it) >= n_units) continue;
-              for (int kb = 0; kb < fwd_nkb(s); ++kb) {
-                mbar_wait(b_wfull + 8 * stage, phase);
-                mbar_arrive_cluster(mapa_u32(b_pfull + 8 * stage, 0));
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-              }
-            }
-        }
-      }
+      // peer CTA of a pair: its tensor core is driven by the leader's cta_group::2 MMAs; nothing to issue here
     }
   } else {
     // ============================== epilogue groups ==============================
@@ -605,6 +603,30 @@ int nb_tc_pack(nb_handle_t h, const nb_mlp_desc* d, const float* params, void* p
   return NB_OK;
 }
 
+// Tensor map over the packed forward blobs for the pair mode, encoded through the driver entry point (no libcuda link).
+static int make_weight_tmap(nb_handle_t h, CUtensorMap* tm, const void* packed) {
+  typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_t enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    NB_CUDA(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !fn) { NB_SET_ERR(h, "cuTensorMapEncodeTiled unavailable"); return NB_ERR_CUDA; }
+    enc = (encode_t)fn;
+  }
+  const cuuint64_t dims[2] = {64, (cuuint64_t)(nb_tc_fwd_packed_bytes() / 128)};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {64, 64};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(packed), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { NB_SET_ERR(h, "cuTensorMapEncodeTiled failed"); return NB_ERR_CUDA; }
+  return NB_OK;
+}
+
 static int launch_fwd(nb_handle_t h, FwdParams& fp, bool train, cudaStream_t st) {
   static bool attr_done[9] = {false, false, false, false, false, false, false, false, false};
   const bool dbg = fp.dbg != nullptr;
@@ -613,6 +635,12 @@ static int launch_fwd(nb_handle_t h, FwdParams& fp, bool train, cudaStream_t st)
   if (mode_env < 0) { const char* e = getenv("NB_TC_CLUSTER"); mode_env = e ? atoi(e) : 2; }
   const int mode = mode_env;
   const bool cta2 = mode != 0;      // launched as clusters of 2
+  if (mode == 1) {
+    static const void* tm_for = nullptr;
+    static CUtensorMap tm;
+    if (tm_for != fp.wpk) { const int rc = make_weight_tmap(h, &tm, fp.wpk); if (rc) return rc; tm_for = fp.wpk; }
+    fp.tmap_w = tm;
+  }
   typedef void (*kern_t)(const FwdParams);
   kern_t kern;
   if (mode == 1) kern = dbg ? mlp_fwd_chain_kernel<false, true, true, false> : (train ? mlp_fwd_chain_kernel<true, false, true, false> : mlp_fwd_chain_kernel<false, false, true, false>);
