@@ -190,6 +190,37 @@ int nb_mse_grad(nb_handle_t h, int64_t N, const float* rgb, const float* target,
 int nb_adam_step(nb_handle_t h, int64_t n, float* p, const float* g, float* m, float* v, float lr, float beta1,
                  float beta2, float eps, int32_t step, void* stream);
 
+/* ---- fused drivers (nb_render_rays) ------------------------------------------ */
+/* Sampling configuration shared by the two drivers below.  lower/span are nb_stratified's [S_c] arrays.
+ * u_mode as in nb_sample_pdf (0: u[S_f] shared = perturb==0, 1: u[N,S_f] injected, 2: Philox);
+ * t_rand NULL => Philox.  offset_c / offset_f are the Philox counters of the coarse / fine draws. */
+typedef struct nb_render_cfg {
+  int32_t S_c, S_f;   /* N_samples_c, N_samples_f (0 = coarse only) */
+  int32_t precision;  /* NB_FP32 / NB_BF16 */
+  int32_t u_mode;
+  uint64_t seed, offset_c, offset_f;
+} nb_render_cfg;
+/* Bytes of caller workspace the drivers need for N rays (train != 0: including the activation stash). */
+int nb_render_workspace_bytes(nb_handle_t h, const nb_mlp_desc* d, int64_t N, const nb_render_cfg* cfg, int32_t train,
+                              size_t* out);
+/* nerf_process.py:185-216 render_rays as one call: stratified -> coarse MLP -> post_process -> sample_pdf -> fine MLP
+ * -> post_process, rays [N,6] (already NDC-warped for llff).  Outputs [N,3]/[N]; any may be NULL.  *_f unused if S_f == 0. */
+int nb_render_rays(nb_handle_t h, const nb_mlp_desc* d, const nb_render_cfg* cfg, const float* params_c, const void* packed_c,
+                   const float* params_f, const void* packed_f, int64_t N, const float* rays, const float* lower,
+                   const float* span, const float* t_rand, const float* u, float* rgb_c, float* disp_c, float* rgb_f,
+                   float* disp_f, void* ws, size_t ws_bytes, void* stream);
+/* train.py:53-69 (render, MSE_c + MSE_f with the mean over n_global*3 values, backward) as one call; the optimizer step
+ * is nb_adam_step.  grad_c / grad_f: flat gradient buffers (= or += per `accumulate`); loss[2] += {MSE_c, MSE_f}.
+ * target [N,3]; target_ready: optional cudaEvent_t the stream waits on right before target is first read (lets the
+ * caller's host->device copy of the target overlap the coarse forward).  nets: bit 0 coarse, bit 1 fine -- a call with
+ * nets=1 followed by one with nets=2 on the same untouched workspace equals nets=3 (the caller can start the coarse
+ * gradient all-reduce in between). */
+int nb_train_rays(nb_handle_t h, const nb_mlp_desc* d, const nb_render_cfg* cfg, const float* params_c, const void* packed_c,
+                  const float* params_f, const void* packed_f, int64_t N, const float* rays, const float* target,
+                  void* target_ready, int64_t n_global, const float* lower, const float* span, const float* t_rand,
+                  const float* u, float* grad_c, float* grad_f, int32_t accumulate, float* loss, float* rgb_c, float* disp_c,
+                  float* rgb_f, float* disp_f, int32_t nets, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- frame output ---------------------------------------------------------- */
 /* test.py:50-61 / utils.py:11: rgb8[N,3] = to8b(rgb), disp8[N] = to8b(disp / nanmax(disp)) on the device.
  * disp8 may be NULL (rgb only); disp_max_scratch is one device float used for the nanmax reduction. */

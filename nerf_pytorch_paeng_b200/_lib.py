@@ -25,9 +25,15 @@ class MlpDesc(C.Structure):
                 ('skip', C.c_int32), ('L_x', C.c_int32), ('L_d', C.c_int32)]
 
 
+class RenderCfg(C.Structure):
+    _fields_ = [('S_c', C.c_int32), ('S_f', C.c_int32), ('precision', C.c_int32), ('u_mode', C.c_int32),
+                ('seed', C.c_uint64), ('offset_c', C.c_uint64), ('offset_f', C.c_uint64)]
+
+
 _p = C.c_void_p
 _i32, _i64, _u64, _f32, _f64, _u32, _sz = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double, C.c_uint, C.c_size_t
 _desc = C.POINTER(MlpDesc)
+_cfg = C.POINTER(RenderCfg)
 
 # name -> (restype, argtypes); mirrors include/nerf_b200.h one to one (tests/test_abi.py checks it)
 SIGNATURES = {
@@ -56,6 +62,10 @@ SIGNATURES = {
     'nb_mlp_tc_probe': (C.c_int, [_p, _desc, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _p]),
     'nb_composite_forward': (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'nb_composite_backward': (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p]),
+    'nb_render_workspace_bytes': (C.c_int, [_p, _desc, _i64, _cfg, _i32, C.POINTER(_sz)]),
+    'nb_render_rays': (C.c_int, [_p, _desc, _cfg, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    'nb_train_rays': (C.c_int, [_p, _desc, _cfg, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _i32, _p,
+                                _p, _p, _p, _p, _i32, _p, _sz, _p]),
     'nb_frame_to8b': (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p]),
     'nb_mse_grad': (C.c_int, [_p, _i64, _p, _p, _f32, _f32, _p, _p, _p]),
     'nb_adam_step': (C.c_int, [_p, _i64, _p, _p, _p, _p, _f32, _f32, _f32, _f32, _i32, _p]),

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import NB_BF16, NB_FP32, MlpDesc, NBError
+from ._lib import NB_BF16, NB_FP32, MlpDesc, NBError, RenderCfg
 
 _engines = {}
 
@@ -39,6 +39,7 @@ class Engine:
             raise NBError(f'nb_create(device={idx}) failed with {rc} (needs an sm_100 GPU)')
         self.h = h
         self._ws = None
+        self._fws = None
         info = (C.c_int32 * 4)()
         self.lib.nb_device_info(self.h, C.byref(info))
         self.sm_count = int(info[0])
@@ -245,6 +246,54 @@ class Engine:
         d_raw = torch.empty_like(raw)
         self._call('nb_composite_backward', n, s, _ptr(raw), _ptr(z), _ptr(rays_d), _ptr(d_rgb), _ptr(d_raw), self.stream)
         return d_raw
+
+    # ------------------------------------------------------------------ fused drivers
+    def _fused_ws(self, desc, n, cfg, train):
+        need = C.c_size_t()
+        self._call('nb_render_workspace_bytes', C.byref(desc), n, C.byref(cfg), 1 if train else 0, C.byref(need))
+        if self._fws is None or self._fws.numel() < need.value:
+            self._fws = None
+            self._fws = torch.empty(need.value + 4096, dtype=torch.uint8, device=self.device)
+        return self._fws
+
+    @staticmethod
+    def _u_mode(u):
+        return 2 if u is None else (0 if u.dim() == 1 else 1)
+
+    def render_rays(self, desc, nets, rays, lower, span, n_fine, precision, t_rand=None, u=None, seed=0, offset_c=0, offset_f=0):
+        """nerf_process.py:185-216 as one nb_render_rays call.  nets = ((flat_c, packed_c), (flat_f, packed_f)).
+        Returns (rgb_c, disp_c, rgb_f, disp_f); the fine pair is None when n_fine == 0."""
+        rays = _chk32(rays, 'rays')
+        n = rays.shape[0]
+        cfg = RenderCfg(lower.numel(), max(int(n_fine), 0), precision, self._u_mode(u), seed, offset_c, offset_f)
+        ws = self._fused_ws(desc, n, cfg, False)
+        (pc, kc), (pf, kf) = nets
+        rgb_c, disp_c = self.empty(n, 3), self.empty(n)
+        rgb_f, disp_f = (self.empty(n, 3), self.empty(n)) if cfg.S_f > 0 else (None, None)
+        self._call('nb_render_rays', C.byref(desc), C.byref(cfg), _ptr(pc), _ptr(kc), _ptr(pf), _ptr(kf), n, _ptr(rays), _ptr(lower),
+                   _ptr(span), _ptr(t_rand), _ptr(u), _ptr(rgb_c), _ptr(disp_c), _ptr(rgb_f), _ptr(disp_f), _ptr(ws), ws.numel(),
+                   self.stream)
+        return rgb_c, disp_c, rgb_f, disp_f
+
+    def train_rays(self, desc, nets, grads, rays, target, n_global, lower, span, n_fine, precision, loss_buf, out, which=3,
+                   t_rand=None, u=None, seed=0, offset_c=0, offset_f=0, accumulate=False, target_ready=None):
+        """train.py:53-69 minus the optimizer as nb_train_rays.  `out` is a dict that receives / supplies the
+        rgb_c, disp_c, rgb_f, disp_f tensors (so a coarse call and a fine call can share it); which = nets bit mask."""
+        rays = _chk32(rays, 'rays')
+        target = _chk32(target, 'target')
+        n = rays.shape[0]
+        cfg = RenderCfg(lower.numel(), max(int(n_fine), 0), precision, self._u_mode(u), seed, offset_c, offset_f)
+        ws = self._fused_ws(desc, n, cfg, True)
+        (pc, kc), (pf, kf) = nets
+        for tag, bit in (('c', 1), ('f', 2)):
+            if which & bit and 'rgb_' + tag not in out:
+                out['rgb_' + tag], out['disp_' + tag] = self.empty(n, 3), self.empty(n)
+        ev = None if target_ready is None else C.c_void_p(target_ready.cuda_event)
+        self._call('nb_train_rays', C.byref(desc), C.byref(cfg), _ptr(pc), _ptr(kc), _ptr(pf), _ptr(kf), n, _ptr(rays), _ptr(target),
+                   ev, int(n_global), _ptr(lower), _ptr(span), _ptr(t_rand), _ptr(u), _ptr(grads[0]), _ptr(grads[1]),
+                   1 if accumulate else 0, _ptr(loss_buf), _ptr(out.get('rgb_c')), _ptr(out.get('disp_c')), _ptr(out.get('rgb_f')),
+                   _ptr(out.get('disp_f')), int(which), _ptr(ws), ws.numel(), self.stream)
+        return out
 
     def frame_to8b(self, rgb, disp=None):
         """test.py:50-61: uint8 frame (and disparity normalised by its nanmax) on the device."""

@@ -66,12 +66,28 @@ class NeRFModule(nn.Module):
         self.slices = None
         self._packed = None
         self._packed_version = None
+        self._plist = None          # cached tuple(self.parameters()); nn.Module traversal is too slow for the per-step path
+        self._flat_dirty = True
+
+    def _apply(self, fn, *a, **k):                       # .to() / .cuda() / .float(): storages may move
+        self._flat_dirty = True
+        return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *a, **k):            # load_state_dict(assign=True) may replace the Parameters
+        self._flat_dirty = True
+        return super()._load_from_state_dict(*a, **k)
 
     # ---- flat parameter storage -------------------------------------------------------------
     def _flatten(self):
         """(Re)build the flat buffer and make every Parameter a view of it.  Called lazily: .to(),
         .cuda() or load_state_dict(assign=True) may have replaced the storages."""
-        params = list(self.parameters())
+        if not self._flat_dirty and self.flat is not None:
+            # fast path: spot-check the two ends of the buffer; the full check below runs after any _apply / load
+            p0, p1 = self._plist[0], self._plist[-1]
+            if p0.data_ptr() == self.flat.data_ptr() and p1.data_ptr() + 4 * p1.numel() == self.flat.data_ptr() + 4 * self.flat.numel():
+                return
+        params = self._plist = tuple(self.parameters())
+        self._flat_dirty = False
         dev = params[0].device
         if dev.type != 'cuda':
             raise NBError('NeRF parameters must live on a CUDA device: there is no CPU fallback')
@@ -108,7 +124,11 @@ class NeRFModule(nn.Module):
         self._flatten()
         if self.flat_grad is None:
             self.flat_grad = torch.zeros_like(self.flat)
-        for p, (o, n, s) in zip(self.parameters(), self.slices):
+        g0, g1 = self._plist[0].grad, self._plist[-1].grad
+        if (g0 is not None and g1 is not None and g0.data_ptr() == self.flat_grad.data_ptr()
+                and g1.data_ptr() + 4 * g1.numel() == self.flat_grad.data_ptr() + 4 * self.flat_grad.numel()):
+            return self.flat_grad                        # still bound (zero_grad(set_to_none=True) would have cleared both ends)
+        for p, (o, n, s) in zip(self._plist, self.slices):
             g = self.flat_grad[o:o + n].view(s)
             if p.grad is None or p.grad.data_ptr() != g.data_ptr():
                 p.grad = g
@@ -117,10 +137,11 @@ class NeRFModule(nn.Module):
     def packed_weights(self):
         if self.precision != NB_BF16:
             return None
+        self._flatten()
         eng = get_engine(self.flat.device)
         # Parameters keep their own version counters (set_data), so track those: any in-place update
         # (optimizer.step, load_state_dict) bumps them
-        ver = (self.flat.data_ptr(), self.flat._version) + tuple(p._version for p in self.parameters())
+        ver = (self.flat.data_ptr(), self.flat._version) + tuple(p._version for p in self._plist)
         if self._packed is None or self._packed.device != self.flat.device:
             self._packed = torch.empty(eng.mlp_packed_bytes(self.desc), dtype=torch.uint8, device=self.flat.device)
             self._packed_version = None
@@ -136,12 +157,12 @@ class NeRFModule(nn.Module):
     def forward(self, x):
         """NeRF.py:33-52 on a materialised embedding x[n, input_ch+input_ch_d] -> [n, 4] = [rgb, sigma]."""
         self._flatten()
-        return _MlpFunction.apply(self, ('emb', x), *self.parameters())
+        return _MlpFunction.apply(self, ('emb', x), *self._plist)
 
     def forward_rays(self, rays, z_vals):
         """Fused form used by render_rays: points + both encodings are generated in-kernel."""
         self._flatten()
-        return _MlpFunction.apply(self, ('rays', rays, z_vals), *self.parameters())
+        return _MlpFunction.apply(self, ('rays', rays, z_vals), *self._plist)
 
 
 class NeRF(nn.Module):

@@ -79,6 +79,27 @@ def _fine_z(rays, opts, z_vals, weights):
     return z_fine
 
 
+def _fused_sampling_args(n, opts, device):
+    """Arguments of the fused drivers (nb_render_rays / nb_train_rays) that reproduce _coarse_z followed by _fine_z:
+    same injected draws, same Philox counters in the same order."""
+    lower, span = _coarse_bins(opts, device)
+    n_fine = max(int(opts.N_samples_f), 0)
+    off_c = _next_offset(n * opts.N_samples_c // 4 + 1)
+    u = None
+    off_f = 0
+    if n_fine > 0:
+        if opts.perturb == 0.:
+            key = (n_fine, str(device))
+            if key not in _u_det_cache:
+                _u_det_cache[key] = torch.linspace(0., 1., steps=n_fine, device=device)
+            u = _u_det_cache[key]
+        else:
+            u = _injected(opts, 'u')
+        off_f = _next_offset(n * n_fine // 4 + 1)
+    return dict(lower=lower, span=span, n_fine=n_fine, t_rand=_injected(opts, 't_rand'), u=u, seed=int(getattr(opts, 'seed', 0)),
+                offset_c=off_c, offset_f=off_f)
+
+
 def pre_process(rays, posenc, opts, z_vals=None, weights=None, isFine=False):
     """nerf_process.py:32-85.  Returns (embedded [n_pts, 90], z_vals, rays_d)."""
     fn_posenc, fn_posenc_d = posenc

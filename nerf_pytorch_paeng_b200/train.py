@@ -82,25 +82,29 @@ def train(idx, i_train, images, gt_cam_param, hw, model, criterion, posenc, opti
             pix = torch.from_numpy(select_pixels(idx, img_h, img_w, opts)).to(device, non_blocking=True)
         img = images[i_img]
         img = img if isinstance(img, torch.Tensor) else torch.from_numpy(img)
-        # H2D of the target image (train.py:37-38) on a side stream: it is only needed at the first loss, so the copy
-        # overlaps ray generation and the coarse forward
+        # H2D of the target image (train.py:37-38) and the gather of the selected pixels (rays.py:62) on a side stream:
+        # the target is only needed at the first loss, so both overlap ray generation and the coarse forward
+        from .engine import get_engine
+        main = torch.cuda.current_stream(device)
         side = _side_stream(device)
+        pix_ready = torch.cuda.Event()
+        pix_ready.record(main)
         with torch.cuda.stream(side):
             img_dev = img.to(device=device, dtype=torch.float32, non_blocking=True)
+            side.wait_event(pix_ready)
+            tgt = get_engine(device).gather_rows(img_dev.reshape(-1, 3), pix)
             copied = torch.cuda.Event()
             copied.record(side)
+        tgt.record_stream(main)
+        pix.record_stream(side)
+        target = (tgt, copied)
         rays_o, rays_d = make_o_d_selected(img_w, img_h, gt_intrinsic, pose, pix, ndc=llff, near=1.)
-        from .engine import get_engine
-
-        def target():
-            torch.cuda.current_stream(device).wait_event(copied)
-            img_dev.record_stream(torch.cuda.current_stream(device))
-            return get_engine(device).gather_rows(img_dev.reshape(-1, 3), pix)
     rays = torch.cat((rays_o, rays_d), dim=-1)
 
     fused = isinstance(criterion, torch.nn.MSELoss) or criterion is None
-    if not fused and callable(target):
-        target = target()
+    if not fused and isinstance(target, tuple):
+        torch.cuda.current_stream(device).wait_event(target[1])
+        target = target[0]
     if fused:
         for net in (model.model_coarse, model.model_fine):
             net.bind_flat_grad()

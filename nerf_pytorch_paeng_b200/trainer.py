@@ -79,6 +79,12 @@ def render_losses_and_grads(model, rays, target, opts, n_global=None, want_grads
     s_max = opts.N_samples_c + max(opts.N_samples_f, 0)
     max_pts = int(getattr(opts, 'max_points_per_pass', MAX_POINTS_PER_PASS))
     rays_per_pass = n if (not want_grads or n * s_max <= max_pts) else max(128, (max_pts // s_max) // 128 * 128)
+    if (want_grads and rays_per_pass == n and n > 0 and getattr(opts, 'fused_driver', True)
+            and model.model_coarse.precision == model.model_fine.precision):
+        return _fused_losses_and_grads(eng, model, rays, target, opts, n_global, loss_buf, on_net_done, out)
+    if isinstance(target, tuple):                 # (tensor, ready event) form of train.train
+        torch.cuda.current_stream(rays.device).wait_event(target[1])
+        target = target[0]
     tgt = None
     rng = getattr(opts, 'rng', None)
     parts = {k: [] for k in ('rgb_c', 'disp_c', 'rgb_f', 'disp_f')}
@@ -124,6 +130,32 @@ def render_losses_and_grads(model, rays, target, opts, n_global=None, want_grads
     return out
 
 
+def _fused_losses_and_grads(eng, model, rays, target, opts, n_global, loss_buf, on_net_done, out):
+    """Single-pass case of render_losses_and_grads as one nb_train_rays call (two when a hook wants to run between the
+    coarse and the fine network, e.g. to start the coarse gradient all-reduce)."""
+    n = rays.shape[0]
+    ready = None
+    if isinstance(target, tuple):
+        target, ready = target
+    elif callable(target):
+        target = target()
+    nc, nf = model.model_coarse, model.model_fine
+    use_fine = opts.N_samples_f > 0
+    nets = ((nc.flat_params(), nc.packed_weights()), (nf.flat_params(), nf.packed_weights()) if use_fine else (None, None))
+    grads = (nc.bind_flat_grad(), nf.bind_flat_grad() if use_fine else None)
+    args = NP._fused_sampling_args(n, opts, rays.device)
+    passes = (3 if use_fine else 1,) if on_net_done is None or not use_fine else (1, 2)
+    for which in passes:
+        eng.train_rays(nc.desc, nets, grads, rays, target, n_global, precision=nc.precision, loss_buf=loss_buf, out=out,
+                       which=which, target_ready=ready, **args)
+        ready = None
+        if on_net_done is not None:
+            for net, bit in ((nc, 1), (nf, 2)):
+                if which & bit:
+                    on_net_done(net)
+    return out
+
+
 def train_step(model, optimizer, rays, target, opts, dist_ctx=None):
     """One optimisation step on a ray batch; returns the device tensor [loss_c, loss_f] (global means)."""
     n_global = rays.shape[0] * (dist_ctx.world_size if dist_ctx is not None else 1)
@@ -162,7 +194,7 @@ def render_frame(model, H, W, K, pose, opts, dist_ctx=None, chunk=None):
         pix = torch.arange(s, e, device=pose.device, dtype=torch.int64)
         o, d = eng.raygen(H, W, K, pose, pix_idx=pix, ndc=ndc, ndc_focal=float(K[0][0]), ndc_near=1.)
         rays = torch.cat((o, d), dim=-1)
-        out = render_losses_and_grads_free(model, rays, opts)
+        out = render_rays_fused(model, rays, opts)
         rgb[s - lo:e - lo] = out['rgb_f' if use_fine else 'rgb_c']
         disp[s - lo:e - lo] = out['disp_f' if use_fine else 'disp_c']
     if dist_ctx is not None:
@@ -189,4 +221,18 @@ def render_losses_and_grads_free(model, rays, opts):
         tag = 'f' if fine else 'c'
         out['rgb_' + tag], out['disp_' + tag] = rgb, disp
         z_prev, w_prev = z, w
+    return out
+
+
+def render_rays_fused(model, rays, opts):
+    """The same render as one nb_render_rays call (the route render_frame takes)."""
+    eng = get_engine(rays.device)
+    nc, nf = model.model_coarse, model.model_fine
+    use_fine = opts.N_samples_f > 0
+    nets = ((nc.flat_params(), nc.packed_weights()), (nf.flat_params(), nf.packed_weights()) if use_fine else (None, None))
+    rgb_c, disp_c, rgb_f, disp_f = eng.render_rays(nc.desc, nets, rays, precision=nc.precision,
+                                                   **NP._fused_sampling_args(rays.shape[0], opts, rays.device))
+    out = {'rgb_c': rgb_c, 'disp_c': disp_c}
+    if use_fine:
+        out['rgb_f'], out['disp_f'] = rgb_f, disp_f
     return out

@@ -370,3 +370,73 @@ def test_training_converges_bf16():
             last = float(loss[1]) if last is None else min(last, float(loss[1]))
     assert np.isfinite(last) and last < (first / 2) / 3, (first, last)
     assert -10 * np.log10(last) > 15., last
+
+
+@pytest.mark.parametrize('precision,perturb,s_f', [('bf16', 1., 128), ('fp32', 0., 128), ('bf16', 1., 0)])
+def test_fused_drivers_equal_stepwise_calls(precision, perturb, s_f):
+    """nb_train_rays / nb_render_rays (one C-ABI call) == the same stages enqueued one by one: identical renders (same kernels,
+    same Philox counters), gradients equal up to the order of the fp32 atomics; split coarse/fine calls == one call."""
+    from nerf_pytorch_paeng_b200 import nerf_process as NP, trainer
+    from nerf_pytorch_paeng_b200.model import NeRF
+    dev = torch.device('cuda', 0)
+    torch.manual_seed(3)
+    model = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).to(dev)
+    model.set_precision(precision)
+    n = 300
+    rays = torch.cat([torch.randn(n, 3, device=dev) * .1 + torch.tensor([0., 0., 4.], device=dev),
+                      torch.nn.functional.normalize(torch.randn(n, 3, device=dev) * .2 + torch.tensor([0., 0., -1.], device=dev), dim=-1)], -1)
+    tgt = torch.rand(n, 3, device=dev)
+    res = {}
+    for mode in ('steps', 'fused', 'split'):
+        opts = make_opts(perturb=perturb, N_samples_f=s_f, seed=11, fused_driver=mode != 'steps')
+        NP._counter[0] = 0
+        for net in (model.model_coarse, model.model_fine):
+            net.bind_flat_grad().zero_()
+        hooks = []
+        out = trainer.render_losses_and_grads(model, rays, tgt, opts, n_global=2 * n,
+                                              on_net_done=(lambda net: hooks.append(net)) if mode == 'split' else None)
+        torch.cuda.synchronize()
+        if mode == 'split':
+            assert hooks == ([model.model_coarse, model.model_fine] if s_f else [model.model_coarse])
+        res[mode] = ({k: v.clone() for k, v in out.items()}, model.model_coarse.flat_grad.clone(), model.model_fine.flat_grad.clone())
+        NP._counter[0] = 0
+        fr = trainer.render_rays_fused(model, rays, opts)
+        NP._counter[0] = 0
+        st = trainer.render_losses_and_grads_free(model, rays, opts)
+        assert set(fr) == set(st)
+        for k in fr:
+            assert torch.equal(fr[k], st[k]), k
+    ref_out, ref_gc, ref_gf = res['steps']
+    for mode in ('fused', 'split'):
+        o, gc, gf = res[mode]
+        assert set(o) == set(ref_out)
+        for k in ref_out:
+            if k == 'loss_buf':
+                assert torch.allclose(o[k], ref_out[k], rtol=1e-5, atol=1e-8)
+            else:
+                assert torch.equal(o[k], ref_out[k]), (mode, k)
+        assert float((gc - ref_gc).norm() / ref_gc.norm()) < 1e-4
+        if s_f:
+            assert float((gf - ref_gf).norm() / ref_gf.norm()) < 1e-4
+        else:
+            assert float(gf.abs().max()) == 0.
+
+
+def test_fused_driver_rejects_small_workspace():
+    from nerf_pytorch_paeng_b200._lib import RenderCfg, NB_BF16
+    from nerf_pytorch_paeng_b200.engine import NBError, get_engine, _ptr
+    from nerf_pytorch_paeng_b200.model import NeRF
+    import ctypes as C
+    dev = torch.device('cuda', 0)
+    eng = get_engine(dev)
+    m = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).to(dev).model_coarse
+    cfg = RenderCfg(64, 128, NB_BF16, 2, 0, 0, 0)
+    need = C.c_size_t()
+    eng._call('nb_render_workspace_bytes', C.byref(m.desc), 256, C.byref(cfg), 0, C.byref(need))
+    assert need.value > 256 * 192 * 16
+    ws = torch.empty(1024, dtype=torch.uint8, device=dev)
+    rays = torch.zeros(256, 6, device=dev)
+    lo = torch.zeros(64, device=dev)
+    with pytest.raises(NBError, match='workspace'):
+        eng._call('nb_render_rays', C.byref(m.desc), C.byref(cfg), _ptr(m.flat_params()), None, _ptr(m.flat_params()), None, 256, _ptr(rays),
+                  _ptr(lo), _ptr(lo), None, None, None, None, None, None, _ptr(ws), ws.numel(), eng.stream)
