@@ -459,6 +459,10 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
           // would otherwise spend waiting for its next accumulator.  (A cp.async.bulk store here made the weight loads
           // queue behind 64 KB of TMA traffic per step: the MMA issuer then waited 45% of its time for weight stages.)
           const uint32_t n16 = ((s == 9) ? 2u : 4u) * (kBlobBytes / 16u);
+          if (p.abl & 32) {           // experiment: TMA bulk store instead of the thread copy
+            if (grp_tid == 0) { bulk_s2g(gdst, act_base, n16 * 16u); bulk_commit(); }
+            store_pending = true;
+          } else if (!(p.abl & 16))
           for (uint32_t i = (uint32_t)grp_tid; i < n16; i += kEpiThreads) {
             uint4 w;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(act_base + i * 16u));
