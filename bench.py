@@ -270,11 +270,15 @@ def run_ours(args):
             return ev_pair('wgrad', lambda: ob(*a, **k))
         ev_pair('dgrad', lambda: ob(*a, stage=1, **k))
         return ev_pair('wgrad', lambda: ob(*a, stage=2, **k))
-    eng.mlp_forward, eng.mlp_backward = fwd_timed, bwd_timed
     n_prof = min(args.steps, 5)
+    opts.fused_driver = False         # same kernels, enqueued stage by stage so that events can be placed between them
+    step(0)                           # untimed: lets the caching allocator create the stage-by-stage buffers
+    torch.cuda.synchronize()
+    eng.mlp_forward, eng.mlp_backward = fwd_timed, bwd_timed
     for i in range(n_prof):
         step(i)
     torch.cuda.synchronize()
+    opts.fused_driver = True
     eng.mlp_forward, eng.mlp_backward = of, ob
     ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in pend.items()}
     avg = {k: (sum(v) / len(v) if v else 0.0) for k, v in ms.items()}
@@ -287,8 +291,8 @@ def run_ours(args):
         traffic = json.load(open(tpath))
     flop_step = FLOP_PER_POINT_TRAIN * N_RAYS * POINTS_PER_RAY
     fwd_tf = FLOP_PER_POINT_FWD * pts_per_launch / (avg['fwd'] / 1e3) / 1e12
-    # wgrad: algorithmic HBM bytes = every 16 KB operand blob its 14 jobs read: 93 blobs per 128-point tile
-    WGRAD_BYTES_PER_POINT = 93 * 16384 / 128.0
+    # wgrad: algorithmic HBM bytes = every 16 KB operand blob its 12 jobs read: 85 blobs per 128-point tile
+    WGRAD_BYTES_PER_POINT = 85 * 16384 / 128.0
     other = {'mlp_fwd_chain_kernel<train>': {'bound': 'tensor', 'achieved': fwd_tf, 'unit': 'TFLOP/s', 'frac': fwd_tf / peak_tf,
                                              'avg_launch_ms': avg['fwd'], 'traffic': traffic.get('mlp_fwd_chain_kernel_bytes_per_launch')}}
     if args.precision == 'bf16':

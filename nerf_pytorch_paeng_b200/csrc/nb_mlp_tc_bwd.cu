@@ -301,39 +301,58 @@ struct WgradJob {
   float* out;            // dW + column offset, row-major [rows, ld]
   int ld, m_first, m_valid, n_valid;   // rows [m_first, m_valid) x cols [0, n_valid) are written; row m -> out + (m - m_first)*ld
   float* bias_out;       // dY column sums of columns [m_first, m_valid) or nullptr
-  int cta_begin, cta_count;
+  // optional second B operand sharing the same A (view layer: [features | PE(viewdir)]): N2 = 64*n2_blk, accumulated in
+  // TMEM columns 256.. (needs m_blk == 2), written to out2
+  const uint8_t* b2;
+  int b2_blobs, b2_first, n2_blk, n2_valid;
+  float* out2;
+  // optional rank-1 rider on the B operand (density head on the last trunk activation): sig_out[k] += sum_p d_raw[p][3] * B[p][k]
+  // and sig_bias += sum_p d_raw[p][3], on the CUDA cores of the bias warps, so that B is not streamed a second time
+  const float* sig_draw;
+  float* sig_out;
+  float* sig_bias;
+  int weight;            // operand blobs streamed per unit (64 points)
+  long long work_begin;  // sum of weight * n_units over the preceding jobs
 };
-struct WgradParams { WgradJob job[kMaxJobs]; int n_jobs; long long n_tiles; };
+struct WgradParams { WgradJob job[kMaxJobs]; int n_jobs; long long n_tiles; long long n_points; long long total_work; };
 
 constexpr int kWgThreads = 192;                         // warp0 producer, warp1 MMA, warps 2-5 bias sums + epilogue
 constexpr int kWgStages = 3;
 constexpr uint32_t kWgStageBytes = 8 * 8192;            // up to 4 A + 4 B half-blobs (64 points x 128 B)
 constexpr uint32_t kWgOffBar = kWgStages * kWgStageBytes;
-constexpr uint32_t kWgSmemBytes = kWgOffBar + 256 + 1024;
+constexpr uint32_t kWgOffSig = kWgOffBar + 256;         // [kWgStages][64] fp32 d_sigma of the stage's points
+constexpr uint32_t kWgSmemBytes = kWgOffSig + kWgStages * 256 + 1024;
+
+// One CTA's share of a job: the kernel's work is the concatenation over jobs of n_units units costing `weight` (operand
+// blobs per unit) each; CTA c owns the slice [total*c/G, total*(c+1)/G) of that line and a unit belongs to the CTA that
+// holds its first blob.  So every CTA streams the same number of bytes (+-1 unit) and at most n_jobs-1 CTAs straddle a job
+// boundary (they flush their accumulator and continue with the next job).
+__device__ __forceinline__ bool wg_segment(const WgradParams& p, int j, long long lo, long long hi, long long n_units, long long& u0,
+                                           long long& u1) {
+  const long long w = p.job[j].weight;
+  const long long a = lo - p.job[j].work_begin, b = hi - p.job[j].work_begin;
+  u0 = a <= 0 ? 0 : (a + w - 1) / w;
+  u1 = b <= 0 ? 0 : (b + w - 1) / w;
+  if (u0 > n_units) u0 = n_units;
+  if (u1 > n_units) u1 = n_units;
+  return u0 < u1;
+}
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 mlp_wgrad_kernel(const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_bar = sbase + kWgOffBar;
-  const uint32_t b_full = s_bar, b_empty = s_bar + 32, b_done = s_bar + 64, s_tmem = s_bar + 72;
+  const uint32_t b_full = s_bar, b_empty = s_bar + 32, b_done = s_bar + 64, s_tmem = s_bar + 72, b_free = s_bar + 80;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // which job does this CTA work on
-  int ji = -1;
-  for (int j = 0; j < p.n_jobs; ++j)
-    if ((int)blockIdx.x >= p.job[j].cta_begin && (int)blockIdx.x < p.job[j].cta_begin + p.job[j].cta_count) ji = j;
-  if (ji < 0) return;
-  const WgradJob& J = p.job[ji];
-  const int rank = (int)blockIdx.x - J.cta_begin;
-  // units of work: half tiles (64 points); unit u -> tile u>>1, half u&1
-  const long long n_units = p.n_tiles * 2;
-  const long long my_units = (n_units > rank) ? (n_units - rank + J.cta_count - 1) / J.cta_count : 0;
-  const uint32_t stage_bytes = (uint32_t)(J.m_blk + J.n_blk) * 8192u;
+  const long long n_units = p.n_tiles * 2;          // units of work: half tiles (64 points); unit u -> tile u>>1, half u&1
+  const long long lo = p.total_work * (long long)blockIdx.x / (long long)gridDim.x;
+  const long long hi = p.total_work * ((long long)blockIdx.x + 1) / (long long)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgStages; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1 + 4); }
     mbar_init(b_done, 1);
+    mbar_init(b_free, 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
@@ -346,78 +365,145 @@ mlp_wgrad_kernel(const WgradParams p) {
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (long long i = 0; i < my_units; ++i) {
-        const long long u = rank + i * J.cta_count;
-        const long long tile = u >> 1;
-        const uint32_t half = (uint32_t)(u & 1) * 8192u;
-        mbar_wait(b_empty + 8 * stage, phase ^ 1);
-        mbar_expect_tx(b_full + 8 * stage, stage_bytes);
-        const uint32_t dst = sbase + stage * kWgStageBytes;
-        for (int k = 0; k < J.m_blk; ++k)
-          bulk_g2s(dst + (uint32_t)k * 8192u, J.a + ((size_t)tile * J.a_blobs + J.a_first + k) * kBlobBytes + half, 8192u, b_full + 8 * stage);
-        for (int k = 0; k < J.n_blk; ++k)
-          bulk_g2s(dst + (uint32_t)(J.m_blk + k) * 8192u, J.b + ((size_t)tile * J.b_blobs + J.b_first + k) * kBlobBytes + half, 8192u,
-                   b_full + 8 * stage);
-        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      for (int j = 0; j < p.n_jobs; ++j) {
+        long long u0, u1;
+        if (!wg_segment(p, j, lo, hi, n_units, u0, u1)) continue;
+        const WgradJob& J = p.job[j];
+        const uint32_t stage_bytes = (uint32_t)(J.m_blk + J.n_blk + J.n2_blk) * 8192u;
+        for (long long u = u0; u < u1; ++u) {
+          const long long tile = u >> 1;
+          const uint32_t half = (uint32_t)(u & 1) * 8192u;
+          mbar_wait(b_empty + 8 * stage, phase ^ 1);
+          mbar_expect_tx(b_full + 8 * stage, stage_bytes);
+          const uint32_t dst = sbase + stage * kWgStageBytes;
+          for (int k = 0; k < J.m_blk; ++k)
+            bulk_g2s(dst + (uint32_t)k * 8192u, J.a + ((size_t)tile * J.a_blobs + J.a_first + k) * kBlobBytes + half, 8192u, b_full + 8 * stage);
+          for (int k = 0; k < J.n_blk; ++k)
+            bulk_g2s(dst + (uint32_t)(J.m_blk + k) * 8192u, J.b + ((size_t)tile * J.b_blobs + J.b_first + k) * kBlobBytes + half, 8192u,
+                     b_full + 8 * stage);
+          for (int k = 0; k < J.n2_blk; ++k)
+            bulk_g2s(dst + (uint32_t)(J.m_blk + J.n_blk + k) * 8192u, J.b2 + ((size_t)tile * J.b2_blobs + J.b2_first + k) * kBlobBytes + half,
+                     8192u, b_full + 8 * stage);
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
-    uint32_t stage = 0, phase = 0;
-    const uint32_t idesc = umma_idesc(128, 64 * J.n_blk, 1, 1);      // both operands MN-major
-    const int m_halves = J.m_blk >> 1;
-    for (long long i = 0; i < my_units; ++i) {
-      mbar_wait(b_full + 8 * stage, phase);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = sbase + stage * kWgStageBytes;
-        const uint32_t b_addr = a_addr + (uint32_t)J.m_blk * 8192u;
-        for (int mh = 0; mh < m_halves; ++mh) {
-#pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16)      // 64 points per stage = 4 x K16
-            umma_ss(tmem_base + (uint32_t)mh * 256u, umma_desc(a_addr + (uint32_t)mh * 16384u + k16 * 2048u, 8192, 1024),
-                    umma_desc(b_addr + k16 * 2048u, 8192, 1024), idesc, (i | k16) ? 1u : 0u);
-        }
-        umma_commit(b_empty + 8 * stage);
-        if (i == my_units - 1) umma_commit(b_done);
-      }
-      __syncwarp();
-      if (++stage == kWgStages) { stage = 0; phase ^= 1; }
-    }
-    if (my_units == 0 && lane == 0) mbar_arrive(b_done);
-  } else {
-    // ---- bias column sums from the A stages, then the TMEM -> global epilogue ----
-    const int t = threadIdx.x - 64;          // 0..127: columns 2t, 2t+1 of the dY tile (M = 64*m_blk <= 256)
-    const bool has_col = (2 * t) < 64 * J.m_blk;
-    float bs0 = 0.f, bs1 = 0.f;
-    uint32_t stage = 0, phase = 0;
-    for (long long i = 0; i < my_units; ++i) {
-      mbar_wait(b_full + 8 * stage, phase);
-      if (J.bias_out != nullptr && has_col) {
-        // column pair 2t,2t+1 lives in blob (2t)/64, 16B-chunk ((2t)%64)/8, word ((2t)%8)/2 of every 128-byte row
-        const int blob = (2 * t) >> 6, cc = ((2 * t) & 63) >> 3, wd = ((2 * t) & 7) >> 1;
-        const uint32_t base = sbase + stage * kWgStageBytes + (uint32_t)blob * 8192u;
-#pragma unroll 8
-        for (uint32_t row = 0; row < 64; ++row) {
-          uint32_t w;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + sw128_chunk(row, (uint32_t)cc) + (uint32_t)wd * 4u));
-          bs0 += __uint_as_float(w << 16);
-          bs1 += __uint_as_float(w & 0xFFFF0000u);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(b_empty + 8 * stage);
-      if (++stage == kWgStages) { stage = 0; phase ^= 1; }
-    }
-    if (J.bias_out != nullptr && has_col && my_units > 0) {
-      if (2 * t >= J.m_first && 2 * t < J.m_valid) atomicAdd(J.bias_out + 2 * t - J.m_first, bs0);
-      if (2 * t + 1 >= J.m_first && 2 * t + 1 < J.m_valid) atomicAdd(J.bias_out + 2 * t + 1 - J.m_first, bs1);
-    }
-    // accumulators -> flat gradient
-    mbar_wait(b_done, 0);
-    tc_fence_after();
-    if (my_units > 0) {
-      const uint32_t q = (uint32_t)warp & 3u;
+    uint32_t stage = 0, phase = 0, seg = 0;
+    for (int j = 0; j < p.n_jobs; ++j) {
+      long long u0, u1;
+      if (!wg_segment(p, j, lo, hi, n_units, u0, u1)) continue;
+      const WgradJob& J = p.job[j];
+      const uint32_t idesc = umma_idesc(128, 64 * J.n_blk, 1, 1);      // both operands MN-major
+      const uint32_t idesc2 = umma_idesc(128, J.n2_blk > 0 ? 64 * J.n2_blk : 64, 1, 1);
       const int m_halves = J.m_blk >> 1;
+      if (seg > 0) { mbar_wait(b_free, (seg - 1) & 1); tc_fence_after(); }    // previous segment's accumulator has been drained
+      for (long long u = u0; u < u1; ++u) {
+        mbar_wait(b_full + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = sbase + stage * kWgStageBytes;
+          const uint32_t b_addr = a_addr + (uint32_t)J.m_blk * 8192u;
+          const uint32_t first = (u == u0) ? 0u : 1u;
+          for (int mh = 0; mh < m_halves; ++mh) {
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16)      // 64 points per stage = 4 x K16
+              umma_ss(tmem_base + (uint32_t)mh * 256u, umma_desc(a_addr + (uint32_t)mh * 16384u + k16 * 2048u, 8192, 1024),
+                      umma_desc(b_addr + k16 * 2048u, 8192, 1024), idesc, (first | (uint32_t)k16) ? 1u : 0u);
+          }
+          if (J.n2_blk > 0) {
+            const uint32_t b2_addr = b_addr + (uint32_t)J.n_blk * 8192u;
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16)
+              umma_ss(tmem_base + 256u, umma_desc(a_addr + k16 * 2048u, 8192, 1024), umma_desc(b2_addr + k16 * 2048u, 8192, 1024), idesc2,
+                      (first | (uint32_t)k16) ? 1u : 0u);
+          }
+          umma_commit(b_empty + 8 * stage);
+          if (u == u1 - 1) umma_commit(b_done);
+        }
+        __syncwarp();
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+      ++seg;
+    }
+  } else {
+    // ---- column sums (bias gradients, density-head rider) from the staged operands, then the TMEM -> global flush ----
+    const int t = threadIdx.x - 64;           // 0..127
+    const int chunk = t & 31;                 // 16-byte chunk = 8 consecutive feature columns: blob chunk>>3, chunk-in-row chunk&7
+    const uint32_t rg = (uint32_t)t >> 5;     // row group: points rg*16 .. rg*16+15 of the stage
+    const uint32_t q = (uint32_t)warp & 3u;   // TMEM lane quarter of this warp
+    uint32_t stage = 0, phase = 0, seg = 0;
+    for (int j = 0; j < p.n_jobs; ++j) {
+      long long u0, u1;
+      if (!wg_segment(p, j, lo, hi, n_units, u0, u1)) continue;
+      const WgradJob& J = p.job[j];
+      const bool do_bias = J.bias_out != nullptr && chunk < 8 * J.m_blk;
+      const bool do_sig = J.sig_draw != nullptr;
+      float bs[8], sg[8], sgb = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { bs[k] = 0.f; sg[k] = 0.f; }
+      float ds_next = 0.f;
+      if (do_sig && t < 64) { const long long pt = u0 * 64 + t; ds_next = pt < p.n_points ? J.sig_draw[pt * 4 + 3] : 0.f; }
+      for (long long u = u0; u < u1; ++u) {
+        const uint32_t sig = sbase + kWgOffSig + stage * 256u;
+        if (do_sig) {
+          // d_sigma of this stage's 64 points -> shared (rows past the last point contribute nothing); next unit's prefetched
+          if (t < 64) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sig + (uint32_t)t * 4u), "f"(ds_next) : "memory");
+          named_bar_sync(1, 128);
+          if (t < 64 && u + 1 < u1) { const long long pt = (u + 1) * 64 + t; ds_next = pt < p.n_points ? J.sig_draw[pt * 4 + 3] : 0.f; }
+        }
+        mbar_wait(b_full + 8 * stage, phase);
+        const uint32_t st_base = sbase + stage * kWgStageBytes;
+        if (do_bias) {
+          const uint32_t base = st_base + (uint32_t)(chunk >> 3) * 8192u;
+#pragma unroll 4
+          for (uint32_t r = 0; r < 16; ++r) {
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                         : "r"(base + sw128_chunk(rg * 16u + r, (uint32_t)chunk & 7u)));
+            bs[0] += __uint_as_float(w0 << 16); bs[1] += __uint_as_float(w0 & 0xFFFF0000u);
+            bs[2] += __uint_as_float(w1 << 16); bs[3] += __uint_as_float(w1 & 0xFFFF0000u);
+            bs[4] += __uint_as_float(w2 << 16); bs[5] += __uint_as_float(w2 & 0xFFFF0000u);
+            bs[6] += __uint_as_float(w3 << 16); bs[7] += __uint_as_float(w3 & 0xFFFF0000u);
+          }
+        }
+        if (do_sig) {     // B operand (N = 256 = 32 chunks): every thread has a chunk
+          const uint32_t base = st_base + (uint32_t)(J.m_blk + (chunk >> 3)) * 8192u;
+#pragma unroll 4
+          for (uint32_t r = 0; r < 16; ++r) {
+            uint32_t w0, w1, w2, w3;
+            float ds;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                         : "r"(base + sw128_chunk(rg * 16u + r, (uint32_t)chunk & 7u)));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ds) : "r"(sig + (rg * 16u + r) * 4u));
+            sg[0] = fmaf(ds, __uint_as_float(w0 << 16), sg[0]); sg[1] = fmaf(ds, __uint_as_float(w0 & 0xFFFF0000u), sg[1]);
+            sg[2] = fmaf(ds, __uint_as_float(w1 << 16), sg[2]); sg[3] = fmaf(ds, __uint_as_float(w1 & 0xFFFF0000u), sg[3]);
+            sg[4] = fmaf(ds, __uint_as_float(w2 << 16), sg[4]); sg[5] = fmaf(ds, __uint_as_float(w2 & 0xFFFF0000u), sg[5]);
+            sg[6] = fmaf(ds, __uint_as_float(w3 << 16), sg[6]); sg[7] = fmaf(ds, __uint_as_float(w3 & 0xFFFF0000u), sg[7]);
+            sgb += ds;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_empty + 8 * stage);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+      if (do_bias) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int col = chunk * 8 + k;
+          if (col >= J.m_first && col < J.m_valid) atomicAdd(J.bias_out + col - J.m_first, bs[k]);
+        }
+      }
+      if (do_sig) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(J.sig_out + chunk * 8 + k, sg[k]);
+        if (chunk == 0) atomicAdd(J.sig_bias, sgb);
+      }
+      // accumulators -> flat gradient
+      mbar_wait(b_done, seg & 1);
+      tc_fence_after();
+      const int m_halves = J.m_blk >> 1;
+      const bool vec4 = (J.ld & 3) == 0 && ((uintptr_t)J.out & 15) == 0 && (J.n_valid & 3) == 0;
       for (int mh = 0; mh < m_halves; ++mh) {
         const int m = mh * 128 + (int)(q * 32u) + lane;          // output row (out-feature)
         for (int c32 = 0; c32 < 2 * J.n_blk; ++c32) {
@@ -426,12 +512,36 @@ mlp_wgrad_kernel(const WgradParams p) {
           tmem_ld_wait();
           if (m >= J.m_first && m < J.m_valid) {
             float* dst = J.out + (size_t)(m - J.m_first) * J.ld + c32 * 32;
+            if (vec4) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c32 * 32 + j < J.n_valid) atomicAdd(dst + j, v[j]);
+              for (int jj = 0; jj < 32; jj += 4)
+                if (c32 * 32 + jj < J.n_valid)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + jj), "f"(v[jj]), "f"(v[jj + 1]), "f"(v[jj + 2]),
+                               "f"(v[jj + 3]) : "memory");
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj)
+                if (c32 * 32 + jj < J.n_valid) atomicAdd(dst + jj, v[jj]);
+            }
           }
         }
       }
+      for (int c32 = 0; c32 < 2 * J.n2_blk; ++c32) {            // second B operand (m_blk == 2): TMEM columns 256..
+        const int m = (int)(q * 32u) + lane;
+        float v[32];
+        tmem_ld32(tmem_base + ((q * 32u) << 16) + 256u + (uint32_t)c32 * 32u, v);
+        tmem_ld_wait();
+        if (m >= J.m_first && m < J.m_valid) {
+          float* dst = J.out2 + (size_t)(m - J.m_first) * J.ld + c32 * 32;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj)
+            if (c32 * 32 + jj < J.n2_valid) atomicAdd(dst + jj, v[jj]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_free);       // the MMA warp may overwrite the accumulator for this CTA's next segment
+      ++seg;
     }
   }
   tc_fence_before();
@@ -544,29 +654,23 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
       }
     }
     // feature layer, view layer, heads
+    // feature layer; the density head (dW_sigma = d_sigma^T h8, db_sigma) rides on its B operand instead of streaming h8 again
     add(w8 + W.off_dfeat, 4, 0, 4, stash + S.off_h[7], 4, 0, 4, grad + L.wf, 256, 0, 256, 256, grad + L.bf);
+    wp.job[nj - 1].sig_draw = d_raw; wp.job[nj - 1].sig_out = grad + L.ws; wp.job[nj - 1].sig_bias = grad + L.bs;
+    // view layer: one job, dg read once against both input blocks [features (256) | PE(viewdir) (27)]
     add(w8 + W.off_dg, 2, 0, 2, stash + S.off_feat, 4, 0, 4, grad + L.wd, 283, 0, 128, 256, grad + L.bd);
-    add(w8 + W.off_dg, 2, 0, 2, stash + S.off_embd, 1, 0, 1, grad + L.wd + 256, 283, 0, 128, 27, nullptr);
-    // heads: A = d_raw blob (cols 0..2 = d_rgb, col 3 = d_sigma), stored twice so that M = 128 is addressable
+    { WgradJob& j = wp.job[nj - 1]; j.b2 = stash + S.off_embd; j.b2_blobs = 1; j.b2_first = 0; j.n2_blk = 1; j.n2_valid = 27;
+      j.out2 = grad + L.wd + 256; weight[nj - 1] += 1; }
+    // rgb head: A = d_raw blob (cols 0..2 = d_rgb), stored twice so that M = 128 is addressable
     add(w8 + W.off_draw, 2, 0, 2, stash + S.off_g, 2, 0, 2, grad + L.wc, 128, 0, 3, 128, grad + L.bc);          // dWc, dbc
-    add(w8 + W.off_draw, 2, 0, 2, stash + S.off_h[7], 4, 0, 4, grad + L.ws, 256, 3, 4, 256, grad + L.bs);       // dWsigma, dbsigma
     wp.n_jobs = nj;
-    // distribute the CTAs over the jobs so that the largest (traffic / CTAs) ratio is as small as possible: start from one CTA
-    // per job and hand out the rest greedily to the currently most loaded job (the kernel ends with its slowest job)
-    int n_cta = h->sm_count;
-    if (n_cta < nj) n_cta = nj;
-    for (int j = 0; j < nj; ++j) wp.job[j].cta_count = 1;
-    for (int given = nj; given < n_cta; ++given) {
-      int worst = 0;
-      double worst_load = -1.0;
-      for (int j = 0; j < nj; ++j) {
-        const double load = (double)weight[j] / wp.job[j].cta_count;
-        if (load > worst_load) { worst_load = load; worst = j; }
-      }
-      wp.job[worst].cta_count++;
-    }
-    int begin = 0;
-    for (int j = 0; j < nj; ++j) { wp.job[j].cta_begin = begin; begin += wp.job[j].cta_count; }
+    wp.n_points = P;
+    // every CTA streams an equal slice of the concatenated job list (wg_segment)
+    long long work = 0;
+    for (int j = 0; j < nj; ++j) { wp.job[j].weight = weight[j]; wp.job[j].work_begin = work; work += (long long)weight[j] * n_tiles * 2; }
+    wp.total_work = work;
+    int begin = h->sm_count;
+    if ((long long)begin > n_tiles * 2) begin = (int)(n_tiles * 2);
     mlp_wgrad_kernel<<<begin, kWgThreads, kWgSmemBytes, st>>>(wp);
     NB_LAUNCHED(h);
   }

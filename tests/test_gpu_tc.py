@@ -197,8 +197,8 @@ def emulate_backward(p, st, d_raw, P):
     db = bf16(d)
     grads['linear_color.weight'] = db[:, :3].T @ st['g']
     grads['linear_color.bias'] = db[:, :3].sum(0)
-    grads['linear_density.weight'] = db[:, 3:4].T @ st['h7']
-    grads['linear_density.bias'] = db[:, 3:4].sum(0)
+    grads['linear_density.weight'] = d[:, 3:4].T @ st['h7']          # fp32 d_sigma: CUDA-core rider of the feature-layer wgrad job
+    grads['linear_density.bias'] = d[:, 3:4].sum(0)
     grads['linear_d.weight'] = np.concatenate([dg.T @ st['feat'], dg.T @ st['embd'][:, :27]], 1)
     grads['linear_d.bias'] = dg.sum(0)
     dfeat = bf16(dg @ Wb['linear_d.weight'][:, :256])
