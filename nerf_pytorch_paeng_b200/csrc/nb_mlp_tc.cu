@@ -158,7 +158,7 @@ __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begi
     }
     const float* bc = bias + c32 * 32;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += bc[j];
+    for (int j = 0; j < 32; j += 2) add_f32x2(v[j], v[j + 1], bc[j], bc[j + 1]);      // packed FADD2: half the issue slots
     if (TRAIN && KIND != 3) {
       // ReLU mask of this layer's output for the backward chain, one funnel shift per element: bit (31-j) of the
       // word = SIGN bit of column c32*32+j, i.e. set = inactive.  (An exact +0.0 pre-activation counts as active,

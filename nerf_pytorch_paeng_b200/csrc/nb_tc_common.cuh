@@ -206,6 +206,11 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 }
 
 // byte offset of the 16-byte chunk `c` (0..7) of row `r` inside a SWIZZLE_128B blob of 128-byte rows
+// {a0,a1} += {b0,b1} as one packed fp32x2 add (sm_100 FADD2; same rounding as two scalar adds)
+__device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
 __host__ __device__ __forceinline__ uint32_t sw128_chunk(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
 
 }  // namespace tc
