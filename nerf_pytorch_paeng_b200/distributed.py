@@ -43,6 +43,25 @@ class DistContext:
         """Start the sum all-reduce of one network's flat gradient; returns the work handle (wait() before the optimiser)."""
         return dist.all_reduce(net.bind_flat_grad(), op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
+    def joint_grad_buffer(self, model):
+        """One contiguous fp32 buffer [grad_coarse | grad_fine | loss_c, loss_f]; the two networks' flat gradient buffers
+        become views of it, so a train step needs exactly ONE collective.  (The MLP kernels are persistent and fill every SM's
+        shared memory, so a collective kernel launched "under" them does not overlap -- it runs between two of them.  Fewer
+        collective launches beat earlier ones.)  Returns (whole, loss_view)."""
+        nets = (model.model_coarse, model.model_fine)
+        sizes = [n.flat_params().numel() for n in nets]
+        buf = getattr(self, '_joint', None)
+        if buf is None or buf.numel() != sum(sizes) + 2 or buf.device != nets[0].flat.device:
+            buf = self._joint = torch.zeros(sum(sizes) + 2, dtype=torch.float32, device=nets[0].flat.device)
+        off = 0
+        for n, sz in zip(nets, sizes):
+            view = buf[off:off + sz]
+            if n.flat_grad is None or n.flat_grad.data_ptr() != view.data_ptr():
+                n.flat_grad = view
+            n.bind_flat_grad()
+            off += sz
+        return buf, buf[off:off + 2]
+
     def gather_rows(self, local, n_total):
         """All-gather variable-length row bands (dim 0) into the full [n_total, ...] tensor."""
         sizes = [shard_range(n_total, r, self.world_size) for r in range(self.world_size)]

@@ -5,6 +5,8 @@ Adam) without autograd: every stage is one call into libnerf_b200.so, gradients 
 fp32 buffer per network (so data-parallel training is a single NCCL all-reduce over it), and Adam
 runs over the flat parameter buffer.  ``render_frame`` is test.py:38-40 (make_o_d -> batchify).
 """
+import os
+
 import torch
 
 from . import nerf_process as NP
@@ -157,21 +159,33 @@ def _fused_losses_and_grads(eng, model, rays, target, opts, n_global, loss_buf, 
 
 
 def train_step(model, optimizer, rays, target, opts, dist_ctx=None):
-    """One optimisation step on a ray batch; returns the device tensor [loss_c, loss_f] (global means)."""
+    """One optimisation step on a ray batch; returns the device tensor [loss_c, loss_f] (global means).
+
+    Data parallel (dist_ctx): every rank normalises by the global ray count, the two flat gradient buffers and the two
+    losses live in one joint buffer and are summed by a single all-reduce.  NB_DP_MODE=overlap restores the earlier
+    schedule (coarse all-reduce launched before the fine pass, three collectives per step) for comparison."""
     n_global = rays.shape[0] * (dist_ctx.world_size if dist_ctx is not None else 1)
-    works = []
-    hook = None
-    if dist_ctx is not None:
-        # the two networks' gradients are independent (nerf_process.py:66 detaches the fine samples): the coarse
-        # net's all-reduce is launched as soon as its backward is enqueued and overlaps the whole fine pass
-        hook = lambda net: works.append(dist_ctx.allreduce_grad_async(net))
-    out = render_losses_and_grads(model, rays, target, opts, n_global=n_global, on_net_done=hook)
-    if dist_ctx is not None:
+    if dist_ctx is None:
+        out = render_losses_and_grads(model, rays, target, opts, n_global=n_global)
+        optimizer.step()
+        return out['loss_buf']
+    mode = os.environ.get('NB_DP_MODE', 'joint')
+    if mode == 'overlap':
+        works = []
+        out = render_losses_and_grads(model, rays, target, opts, n_global=n_global,
+                                      on_net_done=lambda net: works.append(dist_ctx.allreduce_grad_async(net)))
         dist_ctx.allreduce_(out['loss_buf'])
         for w in works:
             w.wait()
+        optimizer.step()
+        return out['loss_buf']
+    whole, loss = dist_ctx.joint_grad_buffer(model)
+    loss.zero_()
+    render_losses_and_grads(model, rays, target, opts, n_global=n_global, loss_buf=loss)
+    if mode != 'none':               # 'none': no collective at all (timing experiments only; ranks diverge)
+        dist_ctx.allreduce_(whole)
     optimizer.step()
-    return out['loss_buf']
+    return loss
 
 
 @torch.no_grad()
