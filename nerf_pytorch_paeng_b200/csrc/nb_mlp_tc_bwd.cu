@@ -11,9 +11,11 @@
 //  (2) wgrad -- dW_l = dY_l^T . X_l reduced over all points.  The stashed blobs ([128 points x 64 features],
 //      128B-swizzled) are exactly UMMA "MN-major" operands, so both A = dY_l and B = X_l are bulk-loaded and fed
 //      to tcgen05.mma without any transposition; the 256x256 fp32 accumulator of one weight matrix fills the
-//      512 TMEM columns.  The 14 (layer, input-block) jobs run concurrently on disjoint groups of CTAs sized by
-//      their HBM traffic; bias gradients are column sums of the dY tiles taken from shared memory by spare
-//      warps; results are added to the flat fp32 gradient with red.global.add.
+//      512 TMEM columns.  The 12 (layer, input-block) jobs form one line of work cut into equal-traffic slices, one per
+//      CTA (wgrad is HBM-bound: 85 operand blobs per tile, see wg_segment); the view layer's two input blocks share one
+//      job (second accumulator region) and the density head rides on the feature job's B operand; bias gradients are
+//      column sums of the dY tiles taken from shared memory by spare warps; results are added to the flat fp32
+//      gradient with red.global.add (v4 where the rows are 16-byte aligned).
 #include <stdlib.h>
 #include "nb_mlp_tc.h"
 #include "nb_tc_common.cuh"
