@@ -14,6 +14,11 @@ struct nb_handle_s {
   int cc_major, cc_minor;
   long long launches;   // kernels launched through this handle
   char err[512];
+  // per-device lazily initialised state (function attributes are per device; a process may hold one handle per GPU)
+  bool fwd_attr_done[9];
+  bool bwd_attr_done;
+  alignas(64) unsigned char w_tmap[128];   // CUtensorMap of the packed forward weights (pair mode), valid for w_tmap_for
+  const void* w_tmap_for;
 };
 
 #define NB_SET_ERR(h, ...) do { if (h) snprintf((h)->err, sizeof((h)->err), __VA_ARGS__); } while (0)

@@ -632,7 +632,6 @@ static int make_weight_tmap(nb_handle_t h, CUtensorMap* tm, const void* packed) 
 }
 
 static int launch_fwd(nb_handle_t h, FwdParams& fp, bool train, cudaStream_t st) {
-  static bool attr_done[9] = {false, false, false, false, false, false, false, false, false};
   const bool dbg = fp.dbg != nullptr;
   // cluster mode: 0 = independent CTAs, 1 = CTA pairs issuing cta_group::2 MMAs, 2 = independent MMAs + multicast weight ring
   static int mode_env = -1;
@@ -640,10 +639,10 @@ static int launch_fwd(nb_handle_t h, FwdParams& fp, bool train, cudaStream_t st)
   const int mode = mode_env;
   const bool cta2 = mode != 0;      // launched as clusters of 2
   if (mode == 1) {
-    static const void* tm_for = nullptr;
-    static CUtensorMap tm;
-    if (tm_for != fp.wpk) { const int rc = make_weight_tmap(h, &tm, fp.wpk); if (rc) return rc; tm_for = fp.wpk; }
-    fp.tmap_w = tm;
+    static_assert(sizeof(CUtensorMap) <= sizeof(h->w_tmap), "tensor map does not fit the handle slot");
+    CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(h->w_tmap);
+    if (h->w_tmap_for != fp.wpk) { const int rc = make_weight_tmap(h, tm, fp.wpk); if (rc) return rc; h->w_tmap_for = fp.wpk; }
+    fp.tmap_w = *tm;
   }
   typedef void (*kern_t)(const FwdParams);
   kern_t kern;
@@ -651,9 +650,9 @@ static int launch_fwd(nb_handle_t h, FwdParams& fp, bool train, cudaStream_t st)
   else if (mode == 2) kern = dbg ? mlp_fwd_chain_kernel<false, true, false, true> : (train ? mlp_fwd_chain_kernel<true, false, false, true> : mlp_fwd_chain_kernel<false, false, false, true>);
   else kern = dbg ? mlp_fwd_chain_kernel<false, true, false, false> : (train ? mlp_fwd_chain_kernel<true, false, false, false> : mlp_fwd_chain_kernel<false, false, false, false>);
   const int ki = (dbg ? 2 : (train ? 1 : 0)) + 3 * mode;
-  if (!attr_done[ki]) {
+  if (!h->fwd_attr_done[ki]) {
     NB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_done[ki] = true;
+    h->fwd_attr_done[ki] = true;
   }
   NB_CUDA(h, cudaMemcpyToSymbolAsync(c_fw, fp.wpk + nb_tc_small_offset(), sizeof(TcSmall), 0, cudaMemcpyDeviceToDevice, st));
   const long long n_tiles = (fp.P + 127) / 128;

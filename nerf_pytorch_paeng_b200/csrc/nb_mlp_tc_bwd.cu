@@ -585,12 +585,11 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
   if (!accumulate && (stages & 1)) NB_CUDA(h, cudaMemsetAsync(grad, 0, L.total * sizeof(float), st));
   const TcStash S = nb_tc_stash_layout(P);
   const long long n_tiles = S.tiles;
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (!h->bwd_attr_done) {
     NB_CUDA(h, cudaFuncSetAttribute(mlp_dgrad_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     NB_CUDA(h, cudaFuncSetAttribute(mlp_dgrad_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     NB_CUDA(h, cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmemBytes));
-    attr_done = true;
+    h->bwd_attr_done = true;
   }
   // ---- (1) dgrad chain
   if (stages & 1) {

@@ -440,3 +440,46 @@ def test_fused_driver_rejects_small_workspace():
     with pytest.raises(NBError, match='workspace'):
         eng._call('nb_render_rays', C.byref(m.desc), C.byref(cfg), _ptr(m.flat_params()), None, _ptr(m.flat_params()), None, 256, _ptr(rays),
                   _ptr(lo), _ptr(lo), None, None, None, None, None, None, _ptr(ws), ws.numel(), eng.stream)
+
+
+def test_data_parallel_path_world_size_1(tmp_path):
+    """The data-parallel train step (joint gradient+loss buffer, one NCCL all-reduce) with a 1-rank process group equals
+    the plain step: same loss, same parameters after Adam.  (2-rank equivalence: test_two_gpu_equals_one_gpu.)"""
+    import copy
+    import torch.distributed as dist
+    from nerf_pytorch_paeng_b200 import nerf_process as NP, trainer
+    from nerf_pytorch_paeng_b200.distributed import DistContext
+    from nerf_pytorch_paeng_b200.model import NeRF
+    dev = torch.device('cuda', 0)
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group('nccl', init_method=f'file://{tmp_path}/pg', rank=0, world_size=1)
+        created = True
+    try:
+        torch.manual_seed(5)
+        m0 = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).to(dev)
+        m0.set_precision('bf16')
+        m1 = copy.deepcopy(m0)
+        n = 256
+        rays = torch.cat([torch.randn(n, 3, device=dev) * .1 + torch.tensor([0., 0., 4.], device=dev),
+                          torch.nn.functional.normalize(torch.randn(n, 3, device=dev) * .2 + torch.tensor([0., 0., -1.], device=dev), dim=-1)], -1)
+        tgt = torch.rand(n, 3, device=dev)
+        res = []
+        for model, ctx in ((m0, None), (m1, DistContext())):
+            opts = make_opts(seed=3)
+            NP._counter[0] = 0
+            opt = trainer.FlatAdam(model, lr=5e-4)
+            losses = [trainer.train_step(model, opt, rays, tgt, opts, dist_ctx=ctx).clone() for _ in range(1)]
+            torch.cuda.synchronize()
+            res.append((torch.stack(losses), model.model_coarse.flat_grad.clone(), model.model_fine.flat_grad.clone(),
+                        model.model_coarse.flat_params().clone()))
+        assert torch.allclose(res[0][0], res[1][0], rtol=1e-4, atol=1e-7)
+        for k in (1, 2):        # gradients of the step (fp32 atomics reorder the sums)
+            assert float((res[0][k] - res[1][k]).norm() / res[0][k].norm()) <= 1e-4
+        # one Adam step moves every parameter by ~lr; identical up to the sign flips of ~zero gradients
+        assert float((res[0][3] - res[1][3]).abs().median()) <= 1e-6
+        whole, loss = DistContext().joint_grad_buffer(m1)
+        assert whole.numel() == 2 * 595844 + 2 and m1.model_fine.flat_grad.data_ptr() == whole[595844:].data_ptr()
+    finally:
+        if created:
+            dist.destroy_process_group()
