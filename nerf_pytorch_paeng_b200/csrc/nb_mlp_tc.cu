@@ -59,8 +59,8 @@ constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;        // + alignment slac
 
 constexpr int kThreads = 576;   // warp 0 producer, warp 1 MMA, 8 epilogue warps per slot (2 per TMEM lane quarter: column halves)
 constexpr int kEpiThreads = 256;
-// measured: per-thread 16-byte stash stores (stride 128 B) free the TMA unit for the weight stream (wait_wfull 45% -> 14%)
-// but triple the epilogue time; the activation tile is therefore bulk-stored from shared memory, in 16 KB pieces.
+// stash route (measured): per-thread 16-byte stores from registers are 3x slower, cp.async.bulk stores starve
+// the weight ring; the tile is copied shared->global by the epilogue threads after they released the MMA warp
 constexpr bool kDirectStash = false;
 constexpr int kBarEpi0 = 1;
 
