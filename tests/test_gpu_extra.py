@@ -483,3 +483,40 @@ def test_data_parallel_path_world_size_1(tmp_path):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_fused_driver_workspace_is_not_overrun():
+    """nb_train_rays stays inside the nb_render_workspace_bytes it announces (guard bands), incl. the activation stash."""
+    import ctypes as C
+    from nerf_pytorch_paeng_b200 import nerf_process as NP
+    from nerf_pytorch_paeng_b200._lib import RenderCfg, NB_BF16
+    from nerf_pytorch_paeng_b200.engine import get_engine, _ptr
+    from nerf_pytorch_paeng_b200.model import NeRF
+    dev = torch.device('cuda', 0)
+    eng = get_engine(dev)
+    torch.manual_seed(1)
+    model = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).to(dev)
+    model.set_precision('bf16')
+    nc, nf = model.model_coarse, model.model_fine
+    n = 131                                                    # ragged: 131*64 and 131*192 points are not tile multiples
+    rays = torch.cat([torch.zeros(n, 3, device=dev) + torch.tensor([0., 0., 4.], device=dev),
+                      torch.nn.functional.normalize(torch.randn(n, 3, device=dev) * .2 + torch.tensor([0., 0., -1.], device=dev), dim=-1)], -1)
+    tgt = torch.rand(n, 3, device=dev)
+    opts = make_opts()
+    lower, span = NP._coarse_bins(opts, dev)
+    cfg = RenderCfg(64, 128, NB_BF16, 2, 9, 0, 100000)
+    need = C.c_size_t()
+    eng._call('nb_render_workspace_bytes', C.byref(nc.desc), n, C.byref(cfg), 1, C.byref(need))
+    G = 4096
+    whole = torch.full((G + need.value + G,), 0x5A, dtype=torch.uint8, device=dev)
+    ws = whole[G:G + need.value]
+    gc, gf = torch.zeros_like(nc.flat_params()), torch.zeros_like(nf.flat_params())
+    loss = torch.zeros(2, device=dev)
+    rgb_f = torch.empty(n, 3, device=dev)
+    eng._call('nb_train_rays', C.byref(nc.desc), C.byref(cfg), _ptr(nc.flat_params()), _ptr(nc.packed_weights()), _ptr(nf.flat_params()),
+              _ptr(nf.packed_weights()), n, _ptr(rays), _ptr(tgt), None, n, _ptr(lower), _ptr(span), None, None, _ptr(gc), _ptr(gf), 0,
+              _ptr(loss), None, None, _ptr(rgb_f), None, 3, _ptr(ws), ws.numel(), eng.stream)
+    torch.cuda.synchronize()
+    assert bool((whole[:G] == 0x5A).all()) and bool((whole[G + need.value:] == 0x5A).all()), 'workspace guard band overwritten'
+    assert torch.isfinite(loss).all() and float(loss.min()) > 0 and torch.isfinite(gc).all() and torch.isfinite(gf).all()
+    assert float(gc.abs().max()) > 0 and float(gf.abs().max()) > 0 and torch.isfinite(rgb_f).all()

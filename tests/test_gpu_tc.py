@@ -342,3 +342,49 @@ def test_tc_cluster_modes(mode):
     env = dict(os.environ, NB_TC_CLUSTER=mode)
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'tc_mode_check.py')], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and 'OK' in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
+
+
+def test_tc_buffers_are_not_overrun(setup):
+    """Guard bands around every caller-owned buffer of the bf16 forward/backward (raw, activation stash, backward workspace,
+    flat gradient) stay intact: the kernels write exactly the bytes the size queries announce (ragged point count, ghost tile)."""
+    import ctypes as C
+    from nerf_pytorch_paeng_b200._lib import NB_BF16
+    from nerf_pytorch_paeng_b200.engine import _ptr
+    eng, net, g = setup
+    m = net.model_coarse
+    m.precision = NB_BF16
+    n, s = 5, 60                                  # 300 points = 3 tiles (ragged) -> ghost tile in the last CTA pair
+    rays, z = make_rays(g, n, s, seed=4)
+    P = n * s
+    flat = m.flat_params()
+    pk = m.packed_weights()
+    act_b, ws_f, ws_b = eng.mlp_bytes(m.desc, P, NB_BF16)
+    G = 4096                                      # guard bytes either side (keeps 1024-byte alignment of the payload)
+    dev = flat.device
+
+    def guarded(nbytes):
+        buf = torch.full((G + nbytes + G,), 0xA5, dtype=torch.uint8, device=dev)
+        return buf, buf[G:G + nbytes]
+
+    raw_all, raw = guarded(P * 16)
+    act_all, act = guarded(act_b)
+    ws_all, ws = guarded(max(ws_f, ws_b))
+    grad_all, grad = guarded(flat.numel() * 4)
+    rays_t, z_t = cu(rays), cu(z)
+    d_raw = cu((np.random.RandomState(1).randn(P, 4) * 1e-2).astype(np.float32))
+    eng._call('nb_mlp_forward_rays', C.byref(m.desc), _ptr(flat), _ptr(pk), n, s, _ptr(rays_t), _ptr(z_t), _ptr(raw), _ptr(act), NB_BF16,
+              _ptr(ws), ws.numel(), eng.stream)
+    eng._call('nb_mlp_backward', C.byref(m.desc), _ptr(flat), _ptr(pk), P, _ptr(act), _ptr(d_raw), _ptr(grad), 0, NB_BF16, _ptr(ws),
+              ws.numel(), eng.stream)
+    torch.cuda.synchronize()
+    for name, whole, nbytes in (('raw', raw_all, P * 16), ('stash', act_all, act_b), ('workspace', ws_all, max(ws_f, ws_b)),
+                                ('grad', grad_all, flat.numel() * 4)):
+        assert bool((whole[:G] == 0xA5).all()) and bool((whole[G + nbytes:] == 0xA5).all()), f'{name}: guard band overwritten'
+    got = grad.view(torch.float32)
+    assert torch.isfinite(got).all() and float(got.abs().max()) > 0
+    # same gradient as through the engine wrapper
+    ref = torch.empty_like(flat)
+    raw2, act2 = eng.mlp_forward(m.desc, flat, pk, NB_BF16, rays=rays_t, z=z_t, save=True)
+    eng.mlp_backward(m.desc, flat, pk, NB_BF16, P, act2, d_raw, ref)
+    torch.cuda.synchronize()
+    assert float((got - ref).norm() / ref.norm()) <= 1e-4
