@@ -54,7 +54,8 @@ def select_pixels(i, img_h, img_w, opts):
 
 def train(idx, i_train, images, gt_cam_param, hw, model, criterion, posenc, optimizer, global_batch_idx, vis, opts,
           dist_ctx=None):
-    model.train()
+    if not model.training:                      # train.py:14 (a full module-tree walk; skipped when already in training mode)
+        model.train()
     device = torch.device(f'cuda:{opts.gpu_ids[opts.rank]}')
     img_h, img_w = hw
     gt_intrinsic, gt_extrinsic = gt_cam_param
