@@ -378,7 +378,7 @@ def run_ours(args):
             'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD_LLFF if llff else WORKLOAD, 'rays_per_gpu': N_RAYS, 'global_rays': N_RAYS * world, 'samples': [S_C, S_F],
-                       'precision': args.precision, 'parallelism': f'ray-sharded data parallel x{world}, NCCL all-reduce of 2x595,844 fp32 grads',
+                       'precision': args.precision, 'parallelism': f'ray-sharded data parallel x{world}, one NCCL all-reduce of 1,191,690 fp32 (gradients of both nets + the two losses)',
                        'l2': 'per-step working set (activation stash >= 5 GB) exceeds the 126 MB L2; ring of 8 distinct ray batches',
                        'loss': float(loss.sum())},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'render': render, 'gpu_launches': int(launches), 'clocks': clocks,
