@@ -85,7 +85,13 @@ def run(precision, steps, log_every):
     gen = np.random.RandomState(3)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    warm = max(steps // 10, 1)
     for it in range(1, steps + 1):
+        # the reference's schedule shape (scheduler.py: linear warm-up 5e-5 -> 5e-4, then cosine back to 5e-5), scaled to `steps`
+        if it <= warm:
+            opt.param_groups[0]['lr'] = 5e-5 + (5e-4 - 5e-5) * it / warm
+        else:
+            opt.param_groups[0]['lr'] = 5e-5 + 0.5 * (5e-4 - 5e-5) * (1 + np.cos(np.pi * (it - warm) / max(steps - warm, 1)))
         i = train_ids[gen.randint(len(train_ids))]
         pix = eng.select_pixels(4096, H, W, seed=11 + i, offset=it * 4096)
         o, d = eng.raygen(H, W, K, poses[i, :3, :4], pix_idx=pix)
