@@ -3,8 +3,9 @@
 // Replaces nerf_process.py:43-60 (coarse z with unconditional jitter) and nerf_process.py:62-67 +
 // 144-182 (mids, pdf, cdf, searchsorted, gather, lerp, cat, sort).  HBM-bound: coarse 536 B/ray,
 // fine 1792 B/ray.  The fine kernel is warp-cooperative: one warp owns one ray, the
-// ray's z / weights / cdf live in shared memory, each lane inverts S_f/32 samples by binary search
-// and the merged S_c+S_f depths are sorted with a shared-memory bitonic network.
+// ray's z / weights / cdf live in shared memory, each lane inverts S_f/32 samples by binary search;
+// the samples are sorted in registers (warp bitonic network) and rank-merged with the sorted coarse depths
+// (generic sizes / unsorted z_c: shared-memory bitonic network over all S_c+S_f values).
 // All contractual fp32 operations are individually rounded (no FMA contraction).
 #include "nb_common.cuh"
 
@@ -46,6 +47,11 @@ stratified_kernel(long long total4, int S, const float* __restrict__ lower, cons
 constexpr int kWarpsPerBlock = 4;
 
 // per-warp smem layout (floats): z[S_c] | cdf[S_c] (S_c-1 knots; holds w during the build) | bins[S_c] | sort[P2]
+// KF > 0: fast path for S_f == 32*KF <= 2*S_c: every lane owns KF consecutive samples, sorts them in registers (bitonic network
+// over the warp: shuffles for strides >= KF), and the sorted samples are MERGED with the (already sorted) coarse depths by
+// rank -- position = own index + number of smaller elements in the other list -- instead of sorting all S_c+S_f values.
+// The result is the same sorted sequence torch.sort produces (values only; ties are indistinguishable).
+template <int KF>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 sample_pdf_kernel(long long N, int S_c, int S_f, int P2, const float* __restrict__ z_c, const float* __restrict__ w_c,
                   const float* __restrict__ u_in, int u_mode, uint2 key, unsigned long long offset,
@@ -106,17 +112,18 @@ sample_pdf_kernel(long long N, int S_c, int S_f, int P2, const float* __restrict
     if (cdf_out) for (int i = lane; i < n_knots; i += 32) cdf_out[ray * n_knots + i] = scdf[i];
 
     // ---- invert the cdf for S_f samples ----
-    for (int j = lane; j < S_f; j += 32) {
-      float u;
-      if (u_mode == 0) u = u_in[j];
-      else if (u_mode == 1) u = u_in[ray * S_f + j];
-      else {
-        const unsigned long long e = (unsigned long long)(ray * S_f + j);
-        const unsigned long long c = offset + (e >> 2);
-        uint4 x = nb_philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 1u, 0u), key);
-        const int q = (int)(e & 3);
-        u = nb_u01(q == 0 ? x.x : q == 1 ? x.y : q == 2 ? x.z : x.w);
-      }
+    constexpr int KFs = KF > 0 ? KF : 1;
+    float own[KFs];
+    auto draw_u = [&](int j) -> float {
+      if (u_mode == 0) return u_in[j];
+      if (u_mode == 1) return u_in[ray * S_f + j];
+      const unsigned long long e = (unsigned long long)(ray * S_f + j);
+      const unsigned long long c = offset + (e >> 2);
+      const uint4 x = nb_philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 1u, 0u), key);
+      const int q = (int)(e & 3);
+      return nb_u01(q == 0 ? x.x : q == 1 ? x.y : q == 2 ? x.z : x.w);
+    };
+    auto invert = [&](int j, float u) -> float {
       // searchsorted(cdf, u, right=True): first index with cdf[idx] > u, in [0, n_knots]
       int lo = 0, hi = n_knots;
       while (lo < hi) {
@@ -131,11 +138,93 @@ sample_pdf_kernel(long long N, int S_c, int S_f, int P2, const float* __restrict
       if (denom < 1e-5f) denom = 1.0f;
       const float t = __fdiv_rn(__fsub_rn(u, cb), denom);
       const float zs = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
-      if (z_fine) ssort[S_c + j] = zs;
       if (z_samples) z_samples[ray * S_f + j] = zs;
       if (inds_out) inds_out[ray * S_f + j] = ind;
+      return zs;
+    };
+    if (KF > 0) {                 // KF consecutive samples per lane (S_f == 32*KF, KF % 4 == 0)
+#pragma unroll
+      for (int r4 = 0; r4 < KFs; r4 += 4) {
+        const int j0 = lane * KFs + r4;
+        float u4[4];
+        if (u_mode == 2) {        // the four draws of one Philox call belong to this lane
+          const unsigned long long e = (unsigned long long)(ray * S_f + j0);
+          const unsigned long long c = offset + (e >> 2);
+          const uint4 x = nb_philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 1u, 0u), key);
+          u4[0] = nb_u01(x.x); u4[1] = nb_u01(x.y); u4[2] = nb_u01(x.z); u4[3] = nb_u01(x.w);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) u4[q] = draw_u(j0 + q);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (r4 + q < KFs) own[r4 + q] = invert(j0 + q, u4[q]);
+      }
+    } else {
+      for (int j = lane; j < S_f; j += 32) {
+        const float zs = invert(j, draw_u(j));
+        if (z_fine) ssort[S_c + j] = zs;
+      }
     }
     if (!z_fine) { __syncwarp(); continue; }   // warp-uniform: samples only
+    if (KF > 0) {
+      // is z_c sorted (it is for stratified depths)?  Otherwise fall through to the full sort below.
+      bool ok = true;
+      for (int i = lane; i + 1 < S_c; i += 32) ok = ok && (sz[i] <= sz[i + 1]);
+      ok = __all_sync(0xffffffffu, ok);
+      if (ok) {
+        // bitonic sort of 32*KF values, element e = lane*KF + r
+#pragma unroll
+        for (int k = 2; k <= 32 * KFs; k <<= 1) {
+#pragma unroll
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j < KFs) {
+#pragma unroll
+              for (int r = 0; r < KFs; ++r) {
+                const int q = r ^ j;
+                if (q > r) {
+                  const bool up = (((lane * KFs + r) & k) == 0);
+                  const float a = own[r], b = own[q];
+                  if ((a > b) == up) { own[r] = b; own[q] = a; }
+                }
+              }
+            } else {
+              const int lj = j / KFs;
+#pragma unroll
+              for (int r = 0; r < KFs; ++r) {
+                const float other = __shfl_xor_sync(0xffffffffu, own[r], lj);
+                const bool up = (((lane * KFs + r) & k) == 0);
+                const bool lower = ((lane & lj) == 0);
+                own[r] = (lower == up) ? fminf(own[r], other) : fmaxf(own[r], other);
+              }
+            }
+          }
+        }
+        __syncwarp();                            // every lane is done reading cdf / bins: their storage now holds the samples
+        float* sS = scdf;                        // S_f <= 2*S_c floats (cdf + bins regions are contiguous)
+#pragma unroll
+        for (int r = 0; r < KFs; ++r) sS[lane * KFs + r] = own[r];
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < KFs; ++r) {           // samples: after every coarse depth <= it (stable: coarse first on ties)
+          const float v = own[r];
+          int lo = 0, hi = S_c;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (sz[mid] <= v) lo = mid + 1; else hi = mid; }
+          ssort[lane * KFs + r + lo] = v;
+        }
+        for (int i = lane; i < S_c; i += 32) {   // coarse depths: after every sample < it
+          const float a = sz[i];
+          int lo = 0, hi = S_f;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (sS[mid] < a) lo = mid + 1; else hi = mid; }
+          ssort[i + lo] = a;
+        }
+        __syncwarp();
+        for (int i = lane; i < S; i += 32) z_fine[ray * S + i] = ssort[i];
+        __syncwarp();
+        continue;
+      }
+#pragma unroll
+      for (int r = 0; r < KFs; ++r) ssort[S_c + lane * KFs + r] = own[r];
+    }
     for (int i = lane; i < S_c; i += 32) ssort[i] = sz[i];
     for (int i = S + lane; i < P2; i += 32) ssort[i] = __int_as_float(0x7f800000);  // +inf padding
     __syncwarp();
@@ -192,13 +281,21 @@ extern "C" int nb_sample_pdf(nb_handle_t h, int64_t N, int32_t S_c, int32_t S_f,
   while (P2 < S_c + S_f) P2 <<= 1;
   const size_t smem = (size_t)kWarpsPerBlock * (3 * S_c + P2) * sizeof(float);
   NB_REQUIRE(h, smem <= 200 * 1024, "nb_sample_pdf: S_c/S_f too large for shared memory");
+  typedef void (*pdf_kernel_t)(long long, int, int, int, const float*, const float*, const float*, int, uint2, unsigned long long,
+                               const float*, const float*, float*, float*, long long*, float*);
+  pdf_kernel_t kern = sample_pdf_kernel<0>;
+  if (z_fine && S_f <= 2 * S_c) {
+    if (S_f == 128) kern = sample_pdf_kernel<4>;
+    else if (S_f == 256) kern = sample_pdf_kernel<8>;
+    else if (S_f == 512) kern = sample_pdf_kernel<16>;
+  }
   if (smem > 48 * 1024)
-    NB_CUDA(h, cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long blocks = (N + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const long long cap = (long long)h->sm_count * 16;
   if (blocks > cap) blocks = cap;
   uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-  sample_pdf_kernel<<<(int)blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+  kern<<<(int)blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
       (long long)N, S_c, S_f, P2, z_c, weights_c, u, u_mode, key, (unsigned long long)offset, cdf_in, bins_in, z_fine,
       z_samples, (long long*)inds, cdf_out);
   NB_LAUNCHED(h);
