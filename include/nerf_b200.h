@@ -36,7 +36,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; only this ABI is exported */
 #endif
 
-#define NB_ABI_VERSION 1
+#define NB_ABI_VERSION 2
 
 typedef struct nb_handle_s* nb_handle_t;
 
@@ -123,10 +123,17 @@ int nb_stratified(nb_handle_t h, int64_t N, int32_t S_c, const float* lower, con
  * bin positions directly instead of mids(z_c) (the stand-alone sample_pdf(bins, weights) entry,
  * nerf_process.py:144; z_c may then be NULL and z_fine must be NULL).  Optional outputs (may be NULL):
  * z_samples [N,S_f] (unsorted, pre-merge), inds [N,S_f] int64 (torch.searchsorted right=True),
- * cdf_out [N,S_c-1].  Summation order: row sum and cumsum accumulate in fp64. */
+ * cdf_out [N,S_c-1].
+ * Summation order of nerf_process.py:150-152 (torch.sum, torch.cumsum): the reference's result depends on the device and,
+ * on CUDA, on the shape of the call.  cdf_rows >= 0: the order of torch's CUDA kernels (fp32; row sum = lane-strided
+ * partial sums + shuffle-down tree, cumsum = Sklansky scan in blocks whose width ATen derives from [rows, S_c-2]) for a call
+ * with cdf_rows rows (0 = N; pass the reference's chunk_rays when N is a larger chunk than the reference would use), so the
+ * cdf and every bin index are bit-identical to the reference on the same device (needs S_c-2 < 128, else as below);
+ * cdf_rows < 0: fp64 accumulation of the row sum and the cumsum (torch's CPU cumsum; the order the CPU fixtures hold). */
 int nb_sample_pdf(nb_handle_t h, int64_t N, int32_t S_c, int32_t S_f, const float* z_c, const float* weights_c,
                   const float* u, int32_t u_mode, uint64_t seed, uint64_t offset, const float* cdf_in,
-                  const float* bins_in, float* z_fine, float* z_samples, int64_t* inds, float* cdf_out, void* stream);
+                  const float* bins_in, float* z_fine, float* z_samples, int64_t* inds, float* cdf_out, int64_t cdf_rows,
+                  void* stream);
 
 /* ---- K3: positional encoding (materialised form) ---------------------------------------- */
 /* model/PositionalEncoding.py:29-30: out[p] = [x, sin(2^k x), cos(2^k x)]_{k<L}; out is [P, 3+6L]. */
@@ -203,6 +210,7 @@ typedef struct nb_render_cfg {
   int32_t precision;  /* NB_FP32 / NB_BF16 */
   int32_t u_mode;
   uint64_t seed, offset_c, offset_f;
+  int64_t cdf_rows;   /* nb_sample_pdf's cdf_rows (summation order of the fine pdf/cdf) */
 } nb_render_cfg;
 /* Bytes of caller workspace the drivers need for N rays (train != 0: including the activation stash). */
 int nb_render_workspace_bytes(nb_handle_t h, const nb_mlp_desc* d, int64_t N, const nb_render_cfg* cfg, int32_t train,

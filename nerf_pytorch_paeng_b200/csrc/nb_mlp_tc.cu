@@ -145,6 +145,7 @@ template <bool TRAIN, bool DBG, int KIND>
 __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begin, int c_end, uint32_t t_addr, uint32_t act_base, uint32_t r,
                                            long long pt, bool valid, uint32_t* mdst, uint8_t* gdst, float& sigma, float (&rgb)[3]) {
   const float* bias = c_fw.bias[s];
+  uint4 mw = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 1
   for (int c32 = c_begin; c32 < c_end; ++c32) {
     float v[32];
@@ -162,11 +163,13 @@ __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begi
     if (TRAIN && KIND != 3) {
       // ReLU mask of this layer's output for the backward chain, one funnel shift per element: bit (31-j) of the
       // word = SIGN bit of column c32*32+j, i.e. set = inactive.  (An exact +0.0 pre-activation counts as active,
-      // where torch's relu' is 0: a measure-zero difference.)
+      // where torch's relu' is 0: a measure-zero difference.)  The (up to) four words of this thread's column half are
+      // kept in registers and leave as ONE 16-byte store after the loop (a warp then writes 512 contiguous bytes).
       uint32_t m = 0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) m = __funnelshift_l(__float_as_uint(v[j]), m, 1);
-      if (mdst != nullptr) mdst[c32] = m;
+      const int k = c32 - c_begin;
+      if (k == 0) mw.x = m; else if (k == 1) mw.y = m; else if (k == 2) mw.z = m; else mw.w = m;
     }
     if (KIND == 1) {            // sigma head on the fp32 post-ReLU trunk output (NeRF.py:43)
       const float* w = c_fw.ws + c32 * 32;
@@ -203,6 +206,8 @@ __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begi
       }
     }
   }
+  if (TRAIN && KIND != 3 && mdst != nullptr)
+    asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(mdst), "r"(mw.x), "r"(mw.y), "r"(mw.z), "r"(mw.w) : "memory");
 }
 
 // CTA2 = true: the kernel runs as thread-block clusters of two CTAs on one TPC and every GEMM is a
@@ -379,6 +384,7 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
       const long long pt = tile * 128 + r;
       const bool valid = pt < p.P;
       const long long pc = valid ? pt : p.P - 1;            // clamp: padded rows compute finite garbage
+      const long long tile_st = (p.abl & 64) ? (tile & 63) : tile;   // experiment: stash writes stay L2-resident
       // ---- layer-0 operand: positional encoding of the point (K3 fused) ----
       float dirx = 0.f, diry = 0.f, dirz = 0.f;
       const long long t_p0 = clock64();
@@ -397,7 +403,7 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
       fence_proxy_async_smem();
       if (TRAIN) {
         named_bar_sync(bar_id, kEpiThreads);
-        if (grp_tid == 0 && tile_ok) { bulk_s2g(p.stash + p.st.off_embx + (size_t)tile * kBlobBytes, aux_base, kBlobBytes); bulk_commit(); }
+        if (grp_tid == 0 && tile_ok) { bulk_s2g(p.stash + p.st.off_embx + (size_t)tile_st * kBlobBytes, aux_base, kBlobBytes); bulk_commit(); }
         store_pending = true;
       }
       if (CTA2) mbar_arrive_cluster(a_ready_addr); else mbar_arrive(b_aready + 8 * slot);
@@ -418,13 +424,14 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
         const int kind = (s == 7) ? 1 : (s == 9 ? 2 : (s == 8 ? 3 : 0));
         uint32_t* mdst = nullptr;
         if (TRAIN && s != 8)
-          mdst = reinterpret_cast<uint32_t*>(p.stash + p.st.off_mask) + (((size_t)(tile_ok ? tile : 0) * 9 + (s < 8 ? s : 8)) * 128 + r) * 8;
+          mdst = reinterpret_cast<uint32_t*>(p.stash + p.st.off_mask) +
+                 ((((size_t)(tile_ok ? tile_st : 0) * 9 + (s < 8 ? s : 8)) * 2 + half) * 128 + r) * 4;     // [tile][9][half][row][4 words]
         const bool wmask = TRAIN && tile_ok;
         const int c0 = half * 4, c1 = half * 4 + 4;            // this warp's 128 of the 256 columns (64 of 128 at step 9)
         uint8_t* gdst = nullptr;
         if (TRAIN && tile_ok) {
           const size_t off = (s < 8 ? p.st.off_h[s] : (s == 8 ? p.st.off_feat : p.st.off_g));
-          gdst = p.stash + off + (size_t)tile * (s == 9 ? 2u : 4u) * kBlobBytes;
+          gdst = p.stash + off + (size_t)tile_st * (s == 9 ? 2u : 4u) * kBlobBytes;
         }
         if (kind == 0) epi_chunks<TRAIN, DBG, 0>(p, s, c0, c1, t_addr, act_base, r, pt, valid, wmask ? mdst : nullptr, gdst, sigma, rgb);
         else if (kind == 1) epi_chunks<TRAIN, DBG, 1>(p, s, c0, c1, t_addr, act_base, r, pt, valid, wmask ? mdst : nullptr, gdst, sigma, rgb);
@@ -442,16 +449,16 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
         }
         fence_proxy_async_smem();
         tc_fence_before();
+        pe_body += clock64() - t_e0;
+        if (s < 9) {      // release the MMA warp first: it needs only every thread's own (fenced) stores, not the group barrier
+          if (CTA2) mbar_arrive_cluster(a_ready_addr); else mbar_arrive(b_aready + 8 * slot);
+        }
         if (TRAIN) {
-          named_bar_sync(bar_id, kEpiThreads);        // the whole A tile (both column halves) is in shared memory
+          named_bar_sync(bar_id, kEpiThreads);        // the whole A tile (both column halves) is in shared memory: stash copies may start
           if (s == 5) {                               // PE(viewdir) tile for wgrad: one 16 KB bulk store per tile
-            if (grp_tid == 0 && tile_ok) { bulk_s2g(p.stash + p.st.off_embd + (size_t)tile * kBlobBytes, aux_base, kBlobBytes); bulk_commit(); }
+            if (grp_tid == 0 && tile_ok) { bulk_s2g(p.stash + p.st.off_embd + (size_t)tile_st * kBlobBytes, aux_base, kBlobBytes); bulk_commit(); }
             store_pending = true;
           }
-        }
-        pe_body += clock64() - t_e0;
-        if (s < 9) {
-          if (CTA2) mbar_arrive_cluster(a_ready_addr); else mbar_arrive(b_aready + 8 * slot);
         }
         if (TRAIN && gdst != nullptr) {
           // Activation stash: the tile is copied shared -> global by the epilogue threads themselves, fully coalesced

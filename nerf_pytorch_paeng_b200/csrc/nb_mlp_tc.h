@@ -14,7 +14,8 @@ struct TcStash {
   size_t off_h[8];             // post-ReLU trunk outputs h0..h7                   : 4 blobs / tile
   size_t off_feat;             // feature layer output                             : 4 blobs / tile
   size_t off_g;                // post-ReLU view layer output (128 wide)           : 2 blobs / tile
-  size_t off_mask;             // ReLU masks: [tile][9 = h0..h7, g][128 rows][8 x u32], bit (31-j) of word c = sign bit of column 32c+j (set = inactive)
+  size_t off_mask;             // ReLU masks: [tile][9 = h0..h7, g][2 column halves][128 rows][4 x u32]; bit (31-j) of word w of half h = sign bit of
+                               // column 128h+32w+j (g, 128 wide: 64h+32w+j, words 2,3 unused), set = inactive
   size_t total;
   long long tiles;
 };

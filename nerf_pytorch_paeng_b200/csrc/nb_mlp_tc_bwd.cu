@@ -76,6 +76,7 @@ struct DgradParams {
   TcStash st;
   uint8_t* ws;              // dY blobs out
   BwdWs w;
+  int abl;                  // NB_TC_ABLATE experiments: 64 = dY tiles written to an L2-resident window
 };
 
 // MC: clusters of two CTAs sharing the W^T stream by multicast (see mlp_fwd_chain_kernel)
@@ -190,12 +191,15 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
       const long long tile = tile_ok ? tile_raw : 0;
       const long long pt = tile_raw * 128 + r;
       const bool valid = pt < p.P;
+      const long long tile_ws = (p.abl & 64) ? (tile & 63) : tile;
       // ---- prologue: dg = (d_rgb . Wc) * (g > 0) -> act K-blocks 0,1 ; d_raw blob -> aux ----
       float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
       if (valid) dr = __ldg(reinterpret_cast<const float4*>(p.d_raw) + pt);   // padded rows carry zero gradient
-      const uint32_t* mrow = reinterpret_cast<const uint32_t*>(p.stash + p.st.off_mask) + ((size_t)tile * 9 * 128 + r) * 8;
-      const uint4 gm = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)8 * 128 * 8));       // mask of g (128 columns)
-      const uint32_t gmw[4] = {gm.x, gm.y, gm.z, gm.w};
+      // masks: [tile][9][2 column halves][128 rows][4 words] (nb_mlp_tc.h); mrow -> this row's words of layer 0, half 0
+      const uint32_t* mrow = reinterpret_cast<const uint32_t*>(p.stash + p.st.off_mask) + ((size_t)tile * 9 * 2 * 128 + r) * 4;
+      const uint4 gm0 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)(8 * 2) * 128 * 4));       // mask of g: columns 0..63 in words x,y
+      const uint4 gm1 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)(8 * 2 + 1) * 128 * 4));   //            columns 64..127
+      const uint32_t gmw[4] = {gm0.x, gm0.y, gm1.x, gm1.y};
       if (store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, kEpi); store_pending = false; }
 #pragma unroll 1
       for (int c = half * 8; c < half * 8 + 8; ++c) {      // dg columns of this half (one K-block)
@@ -219,9 +223,9 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
       fence_proxy_async_smem();
       named_bar_sync(bar_id, kEpi);
       if (grp_tid == 0 && tile_ok) {
-        bulk_s2g(p.ws + p.w.off_dg + (size_t)tile * 2 * kBlobBytes, act_base, 2 * kBlobBytes);
-        bulk_s2g(p.ws + p.w.off_draw + (size_t)tile * 2 * kBlobBytes, aux_base, kBlobBytes);
-        bulk_s2g(p.ws + p.w.off_draw + (size_t)tile * 2 * kBlobBytes + kBlobBytes, aux_base, kBlobBytes);
+        bulk_s2g(p.ws + p.w.off_dg + (size_t)tile_ws * 2 * kBlobBytes, act_base, 2 * kBlobBytes);
+        bulk_s2g(p.ws + p.w.off_draw + (size_t)tile_ws * 2 * kBlobBytes, aux_base, kBlobBytes);
+        bulk_s2g(p.ws + p.w.off_draw + (size_t)tile_ws * 2 * kBlobBytes + kBlobBytes, aux_base, kBlobBytes);
         bulk_commit();
       }
       store_pending = true;
@@ -232,8 +236,8 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
         // ReLU mask of h_{8-b} for this step (b >= 1): 8 words per row, fetched while the MMA runs
         uint32_t mq[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};      // set bit = inactive unit
         if (b >= 1) {
-          const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)(8 - b) * 128 * 8));
-          const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)(8 - b) * 128 * 8) + 1);
+          const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)((8 - b) * 2) * 128 * 4));
+          const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)((8 - b) * 2 + 1) * 128 * 4));
           mq[0] = m0.x; mq[1] = m0.y; mq[2] = m0.z; mq[3] = m0.w; mq[4] = m1.x; mq[5] = m1.y; mq[6] = m1.z; mq[7] = m1.w;
         }
         mbar_wait(b_accready + 8 * slot, par_acc); par_acc ^= 1;
@@ -269,12 +273,12 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        named_bar_sync(bar_id, kEpi);                       // the whole dY tile is in shared memory
-        if (b < kBwdSteps - 1) mbar_arrive(b_aready + 8 * slot);
+        if (b < kBwdSteps - 1) mbar_arrive(b_aready + 8 * slot);     // release the MMA warp first (own stores are fenced above)
+        named_bar_sync(bar_id, kEpi);                       // the whole dY tile is in shared memory: the copy-out may start
         if (tile_ok) {
           // dY tile -> workspace for wgrad: coalesced copy by the epilogue threads after the MMA warp has been released
           // (a cp.async.bulk store here competes with the weight stream for the TMA unit, see nb_mlp_tc.cu)
-          uint8_t* gdst = p.ws + ((b == 0) ? p.w.off_dfeat : p.w.off_dh[8 - b]) + (size_t)tile * 4 * kBlobBytes;
+          uint8_t* gdst = p.ws + ((b == 0) ? p.w.off_dfeat : p.w.off_dh[8 - b]) + (size_t)tile_ws * 4 * kBlobBytes;
           for (uint32_t i = (uint32_t)grp_tid; i < 4u * (kBlobBytes / 16u); i += (uint32_t)kEpi) {
             uint4 w;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(act_base + i * 16u));
@@ -316,7 +320,7 @@ struct WgradJob {
   int weight;            // operand blobs streamed per unit (64 points)
   long long work_begin;  // sum of weight * n_units over the preceding jobs
 };
-struct WgradParams { WgradJob job[kMaxJobs]; int n_jobs; long long n_tiles; long long n_points; long long total_work; };
+struct WgradParams { WgradJob job[kMaxJobs]; int n_jobs; long long n_tiles; long long n_points; long long total_work; int abl; };
 
 constexpr int kWgThreads = 192;                         // warp0 producer, warp1 MMA, warps 2-5 bias sums + epilogue
 constexpr int kWgStages = 3;
@@ -374,17 +378,19 @@ mlp_wgrad_kernel(const WgradParams p) {
         const uint32_t stage_bytes = (uint32_t)(J.m_blk + J.n_blk + J.n2_blk) * 8192u;
         for (long long u = u0; u < u1; ++u) {
           const long long tile = u >> 1;
+          const long long tile_a = (p.abl & 64) ? (tile & 63) : tile;      // experiments: operands from an L2-resident window
+          const long long tile_b = (p.abl & 128) ? (tile & 63) : tile;
           const uint32_t half = (uint32_t)(u & 1) * 8192u;
           mbar_wait(b_empty + 8 * stage, phase ^ 1);
           mbar_expect_tx(b_full + 8 * stage, stage_bytes);
           const uint32_t dst = sbase + stage * kWgStageBytes;
           for (int k = 0; k < J.m_blk; ++k)
-            bulk_g2s(dst + (uint32_t)k * 8192u, J.a + ((size_t)tile * J.a_blobs + J.a_first + k) * kBlobBytes + half, 8192u, b_full + 8 * stage);
+            bulk_g2s(dst + (uint32_t)k * 8192u, J.a + ((size_t)tile_a * J.a_blobs + J.a_first + k) * kBlobBytes + half, 8192u, b_full + 8 * stage);
           for (int k = 0; k < J.n_blk; ++k)
-            bulk_g2s(dst + (uint32_t)(J.m_blk + k) * 8192u, J.b + ((size_t)tile * J.b_blobs + J.b_first + k) * kBlobBytes + half, 8192u,
+            bulk_g2s(dst + (uint32_t)(J.m_blk + k) * 8192u, J.b + ((size_t)tile_b * J.b_blobs + J.b_first + k) * kBlobBytes + half, 8192u,
                      b_full + 8 * stage);
           for (int k = 0; k < J.n2_blk; ++k)
-            bulk_g2s(dst + (uint32_t)(J.m_blk + J.n_blk + k) * 8192u, J.b2 + ((size_t)tile * J.b2_blobs + J.b2_first + k) * kBlobBytes + half,
+            bulk_g2s(dst + (uint32_t)(J.m_blk + J.n_blk + k) * 8192u, J.b2 + ((size_t)tile_b * J.b2_blobs + J.b2_first + k) * kBlobBytes + half,
                      8192u, b_full + 8 * stage);
           if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }
@@ -597,6 +603,7 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
     memset(&dp, 0, sizeof(dp));
     dp.P = P; dp.wpk = (const uint8_t*)packed + nb_tc_fwd_packed_bytes(); dp.prm = params; dp.L = L; dp.d_raw = d_raw;
     dp.stash = (const uint8_t*)act_save; dp.st = S; dp.ws = (uint8_t*)ws; dp.w = W;
+    { const char* e = getenv("NB_TC_ABLATE"); dp.abl = e ? atoi(e) : 0; }   // timing experiments only
     NB_CUDA(h, cudaMemcpyToSymbolAsync(c_bw, (const uint8_t*)packed + nb_tc_small_offset(), sizeof(TcSmall), 0,
                                        cudaMemcpyDeviceToDevice, st));
     static int mode_env = -1;
@@ -630,6 +637,7 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
     WgradParams wp;
     memset(&wp, 0, sizeof(wp));
     wp.n_tiles = n_tiles;
+    { const char* e = getenv("NB_TC_ABLATE"); wp.abl = e ? atoi(e) : 0; }   // timing experiments only
     const uint8_t* stash = (const uint8_t*)act_save;
     const uint8_t* w8 = (const uint8_t*)ws;
     int weight[kMaxJobs];

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 sample_pdf_kernel(long long N, int S_c, int S_f, int P2, const float* __restrict__ z_c, const float* __restrict__ w_c,
                   const float* __restrict__ u_in, int u_mode, uint2 key, unsigned long long offset,
                   const float* __restrict__ cdf_in, const float* __restrict__ bins_in, float* __restrict__ z_fine,
-                  float* __restrict__ z_samples, long long* __restrict__ inds_out, float* __restrict__ cdf_out) {
+                  float* __restrict__ z_samples, long long* __restrict__ inds_out, float* __restrict__ cdf_out, int scan_ntx, int sum_bw) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per_warp = 3 * S_c + P2;
@@ -80,7 +80,50 @@ sample_pdf_kernel(long long N, int S_c, int S_f, int P2, const float* __restrict
       __syncwarp();
     } else {
       // w = weights[1:-1] + 1e-5 ; pdf = w / sum(w) ; cdf = [0, cumsum(pdf)]   (nerf_process.py:150-155)
-      // sum and cumsum accumulate in fp64 (order-independent to fp32 precision; DESIGN.md "summation order")
+      if (scan_ntx > 0) {
+        // ---- the summation ORDER of torch.sum / torch.cumsum on CUDA (ATen Reduce.cuh / ScanUtils.cuh), fp32 throughout, so that the
+        // cdf -- and with it every bin index -- is bit-identical to the reference running on the same device.
+        for (int i = lane; i < n_w; i += 32) scdf[1 + i] = __fadd_rn(w_c[ray * S_c + 1 + i], 1e-5f);
+        __syncwarp();
+        // torch.sum over the last dim (n_w < 128: no input vectorisation): block_width bw = min(2^floor(log2 n_w), 32) lanes, lane x owns
+        // elements x, x+bw, x+2bw, x+3bw in four accumulators combined as ((v0+v1)+v2)+v3, then a shuffle-down tree bw/2 .. 1
+        float p = 0.f;
+        if (lane < sum_bw) {
+          const float v0 = scdf[1 + lane];
+          const float v1 = lane + sum_bw < n_w ? scdf[1 + lane + sum_bw] : 0.f;
+          const float v2 = lane + 2 * sum_bw < n_w ? scdf[1 + lane + 2 * sum_bw] : 0.f;
+          const float v3 = lane + 3 * sum_bw < n_w ? scdf[1 + lane + 3 * sum_bw] : 0.f;
+          p = __fadd_rn(__fadd_rn(__fadd_rn(v0, v1), v2), v3);
+        }
+        for (int o = sum_bw >> 1; o > 0; o >>= 1) p = __fadd_rn(p, __shfl_down_sync(0xffffffffu, p, o));
+        const float total = __shfl_sync(0xffffffffu, p, 0);
+        __syncwarp();
+        for (int i = lane; i < n_w; i += 32) scdf[1 + i] = __fdiv_rn(scdf[1 + i], total);
+        __syncwarp();
+        // torch.cumsum: Sklansky scan over blocks of 2*scan_ntx elements, the running total added to the first element of the next block
+        float* buf = scdf + 1;
+        const int B = 2 * scan_ntx;
+        float carry = 0.f;
+        for (int c0 = 0; c0 < n_w; c0 += B) {
+          const int len = min(B, n_w - c0);
+          if (lane == 0 && c0 > 0) buf[c0] = __fadd_rn(buf[c0], carry);
+          __syncwarp();
+          for (int m = 0; (1 << m) <= scan_ntx; ++m) {
+            const int sft = 1 << m;
+            for (int t = lane; t < scan_ntx && t < len; t += 32) {
+              const int a = ((t >> m) << (m + 1)) | sft;
+              const int ti = a + (t & (sft - 1));
+              if (ti < len) buf[c0 + ti] = __fadd_rn(buf[c0 + ti], buf[c0 + a - 1]);
+            }
+            __syncwarp();
+          }
+          if (c0 + B <= n_w) carry = buf[c0 + B - 1];
+          __syncwarp();
+        }
+        if (lane == 0) scdf[0] = 0.0f;
+        __syncwarp();
+      } else {
+      // sum and cumsum accumulate in fp64 (order-independent to fp32 precision: ATen's CPU cumsum; DESIGN.md "summation order")
       double part = 0.0;
       for (int i = lane; i < n_w; i += 32) {
         float w = __fadd_rn(w_c[ray * S_c + 1 + i], 1e-5f);
@@ -108,6 +151,7 @@ sample_pdf_kernel(long long N, int S_c, int S_f, int P2, const float* __restrict
       }
       if (lane == 0) scdf[0] = 0.0f;
       __syncwarp();
+      }
     }
     if (cdf_out) for (int i = lane; i < n_knots; i += 32) cdf_out[ray * n_knots + i] = scdf[i];
 
@@ -266,10 +310,22 @@ extern "C" int nb_stratified(nb_handle_t h, int64_t N, int32_t S_c, const float*
   return NB_OK;
 }
 
+// Threads per row of ATen's innermost-dim scan kernel for a [num_rows, row_size] input (ScanUtils.cuh,
+// get_log_num_threads_x_inner_scan<uint32_t>, including its unsigned wrap-around for num_rows >> row_size).
+static int aten_scan_threads_x(uint64_t num_rows, uint32_t row_size) {
+  uint32_t lx = 0, ly = 0;
+  while (((uint32_t)1 << lx) < row_size) ++lx;
+  while (ly < 63 && ((uint64_t)1 << ly) < num_rows) ++ly;
+  const uint32_t diff = lx - ly;
+  lx = ((uint32_t)9 + diff) / (uint32_t)2;
+  lx = lx < 4 ? 4 : (lx > 9 ? 9 : lx);
+  return 1 << lx;
+}
+
 extern "C" int nb_sample_pdf(nb_handle_t h, int64_t N, int32_t S_c, int32_t S_f, const float* z_c,
                              const float* weights_c, const float* u, int32_t u_mode, uint64_t seed, uint64_t offset,
                              const float* cdf_in, const float* bins_in, float* z_fine, float* z_samples, int64_t* inds,
-                             float* cdf_out, void* stream) {
+                             float* cdf_out, int64_t cdf_rows, void* stream) {
   NB_ENTER(h);
   NB_REQUIRE(h, N >= 0 && S_c >= 3 && S_f > 0 && S_c + S_f <= 4096, "nb_sample_pdf: bad sizes");
   NB_REQUIRE(h, z_c || (bins_in && !z_fine), "nb_sample_pdf: z_c may be NULL only with bins_in and without z_fine");
@@ -277,12 +333,21 @@ extern "C" int nb_sample_pdf(nb_handle_t h, int64_t N, int32_t S_c, int32_t S_f,
   NB_REQUIRE(h, weights_c || cdf_in, "nb_sample_pdf: need weights or cdf_in");
   NB_REQUIRE(h, u_mode >= 0 && u_mode <= 2 && (u_mode == 2 || u), "nb_sample_pdf: bad u / u_mode");
   if (N == 0) return NB_OK;
+  // summation order of the pdf normalisation and the cdf: torch's CUDA order when it is restated here (row sums without input
+  // vectorisation: S_c-2 < 128), else fp64 accumulation
+  int scan_ntx = 0, sum_bw = 0;
+  const int n_w = S_c - 2;
+  if (cdf_rows >= 0 && n_w >= 1 && n_w < 128) {
+    scan_ntx = aten_scan_threads_x((uint64_t)(cdf_rows > 0 ? cdf_rows : N), (uint32_t)n_w);
+    sum_bw = 1;
+    while (sum_bw * 2 <= n_w && sum_bw < 32) sum_bw <<= 1;
+  }
   int P2 = 1;
   while (P2 < S_c + S_f) P2 <<= 1;
   const size_t smem = (size_t)kWarpsPerBlock * (3 * S_c + P2) * sizeof(float);
   NB_REQUIRE(h, smem <= 200 * 1024, "nb_sample_pdf: S_c/S_f too large for shared memory");
   typedef void (*pdf_kernel_t)(long long, int, int, int, const float*, const float*, const float*, int, uint2, unsigned long long,
-                               const float*, const float*, float*, float*, long long*, float*);
+                               const float*, const float*, float*, float*, long long*, float*, int, int);
   pdf_kernel_t kern = sample_pdf_kernel<0>;
   if (z_fine && S_f <= 2 * S_c) {
     if (S_f == 128) kern = sample_pdf_kernel<4>;
@@ -297,7 +362,7 @@ extern "C" int nb_sample_pdf(nb_handle_t h, int64_t N, int32_t S_c, int32_t S_f,
   uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   kern<<<(int)blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
       (long long)N, S_c, S_f, P2, z_c, weights_c, u, u_mode, key, (unsigned long long)offset, cdf_in, bins_in, z_fine,
-      z_samples, (long long*)inds, cdf_out);
+      z_samples, (long long*)inds, cdf_out, scan_ntx, sum_bw);
   NB_LAUNCHED(h);
   return NB_OK;
 }

@@ -117,8 +117,10 @@ class Engine:
         return z
 
     def sample_pdf(self, z_c, weights_c, n_fine, u=None, seed=0, offset=0, cdf_in=None, bins_in=None, want_fine=True,
-                   want_samples=False, want_inds=False, want_cdf=False):
-        """weights_c is the full [N,S_c] coarse weight tensor (the kernel applies the [...,1:-1] slice)."""
+                   want_samples=False, want_inds=False, want_cdf=False, cdf_rows=0):
+        """weights_c is the full [N,S_c] coarse weight tensor (the kernel applies the [...,1:-1] slice).
+        cdf_rows: summation order of the pdf/cdf (nb_sample_pdf): 0 = torch's CUDA order for this call's N rows, k > 0 = for a
+        call of k rows (the reference's chunk), -1 = fp64 accumulation (torch's CPU order)."""
         if z_c is not None:
             z_c = _chk32(z_c, 'z_vals')
             n, s_c = z_c.shape
@@ -144,7 +146,7 @@ class Engine:
         inds = self.empty(n, n_fine, dtype=torch.int64) if want_inds else None
         cdf = self.empty(n, s_c - 1) if want_cdf else None
         self._call('nb_sample_pdf', n, s_c, n_fine, _ptr(z_c), _ptr(weights_c), _ptr(u), mode, seed, offset, _ptr(cdf_in),
-                   _ptr(bins_in), _ptr(z_f), _ptr(zs), _ptr(inds), _ptr(cdf), self.stream)
+                   _ptr(bins_in), _ptr(z_f), _ptr(zs), _ptr(inds), _ptr(cdf), int(cdf_rows), self.stream)
         return z_f, zs, inds, cdf
 
     # ------------------------------------------------------------------ K3
@@ -260,12 +262,12 @@ class Engine:
     def _u_mode(u):
         return 2 if u is None else (0 if u.dim() == 1 else 1)
 
-    def render_rays(self, desc, nets, rays, lower, span, n_fine, precision, t_rand=None, u=None, seed=0, offset_c=0, offset_f=0):
+    def render_rays(self, desc, nets, rays, lower, span, n_fine, precision, t_rand=None, u=None, seed=0, offset_c=0, offset_f=0, cdf_rows=0):
         """nerf_process.py:185-216 as one nb_render_rays call.  nets = ((flat_c, packed_c), (flat_f, packed_f)).
         Returns (rgb_c, disp_c, rgb_f, disp_f); the fine pair is None when n_fine == 0."""
         rays = _chk32(rays, 'rays')
         n = rays.shape[0]
-        cfg = RenderCfg(lower.numel(), max(int(n_fine), 0), precision, self._u_mode(u), seed, offset_c, offset_f)
+        cfg = RenderCfg(lower.numel(), max(int(n_fine), 0), precision, self._u_mode(u), seed, offset_c, offset_f, int(cdf_rows))
         ws = self._fused_ws(desc, n, cfg, False)
         (pc, kc), (pf, kf) = nets
         rgb_c, disp_c = self.empty(n, 3), self.empty(n)
@@ -276,13 +278,13 @@ class Engine:
         return rgb_c, disp_c, rgb_f, disp_f
 
     def train_rays(self, desc, nets, grads, rays, target, n_global, lower, span, n_fine, precision, loss_buf, out, which=3,
-                   t_rand=None, u=None, seed=0, offset_c=0, offset_f=0, accumulate=False, target_ready=None):
+                   t_rand=None, u=None, seed=0, offset_c=0, offset_f=0, accumulate=False, target_ready=None, cdf_rows=0):
         """train.py:53-69 minus the optimizer as nb_train_rays.  `out` is a dict that receives / supplies the
         rgb_c, disp_c, rgb_f, disp_f tensors (so a coarse call and a fine call can share it); which = nets bit mask."""
         rays = _chk32(rays, 'rays')
         target = _chk32(target, 'target')
         n = rays.shape[0]
-        cfg = RenderCfg(lower.numel(), max(int(n_fine), 0), precision, self._u_mode(u), seed, offset_c, offset_f)
+        cfg = RenderCfg(lower.numel(), max(int(n_fine), 0), precision, self._u_mode(u), seed, offset_c, offset_f, int(cdf_rows))
         ws = self._fused_ws(desc, n, cfg, True)
         (pc, kc), (pf, kf) = nets
         for tag, bit in (('c', 1), ('f', 2)):

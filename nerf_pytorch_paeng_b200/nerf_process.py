@@ -45,6 +45,17 @@ def _next_offset(n):
     return off
 
 
+def _cdf_rows(opts, n):
+    """Summation order of the fine pdf/cdf (nb_sample_pdf's cdf_rows).  Default: torch's CUDA order for the call the REFERENCE
+    would make -- n rows, or opts.chunk_rays when this engine is handed a larger chunk than the reference's batchify loop uses
+    (nerf_process.py:236) -- so bin indices are bit-identical to the reference on the same device.  opts.cdf_order = 'fp64'
+    selects fp64 accumulation (torch's CPU cumsum; what the CPU-generated fixtures hold)."""
+    if getattr(opts, 'cdf_order', 'cuda') == 'fp64':
+        return -1
+    chunk = int(getattr(opts, 'chunk_rays', 0) or 0)
+    return min(int(n), chunk) if chunk > 0 else int(n)
+
+
 def _injected(opts, name):
     rng = getattr(opts, 'rng', None)
     return None if rng is None else rng.get(name)
@@ -75,7 +86,7 @@ def _fine_z(rays, opts, z_vals, weights):
     else:
         u = _injected(opts, 'u')
     z_fine, _, _, _ = eng.sample_pdf(z_vals, weights.detach(), opts.N_samples_f, u=u, seed=int(getattr(opts, 'seed', 0)),
-                                     offset=_next_offset(n * opts.N_samples_f // 4 + 1))
+                                     offset=_next_offset(n * opts.N_samples_f // 4 + 1), cdf_rows=_cdf_rows(opts, n))
     return z_fine
 
 
@@ -97,7 +108,7 @@ def _fused_sampling_args(n, opts, device):
             u = _injected(opts, 'u')
         off_f = _next_offset(n * n_fine // 4 + 1)
     return dict(lower=lower, span=span, n_fine=n_fine, t_rand=_injected(opts, 't_rand'), u=u, seed=int(getattr(opts, 'seed', 0)),
-                offset_c=off_c, offset_f=off_f)
+                offset_c=off_c, offset_f=off_f, cdf_rows=_cdf_rows(opts, n))
 
 
 def pre_process(rays, posenc, opts, z_vals=None, weights=None, isFine=False):
@@ -156,7 +167,8 @@ def sample_pdf(bins, weights, N_samples, det=False, opts=None):
     else:
         u = _injected(opts, 'u')
     _, samples, _, _ = eng.sample_pdf(None, w_pad, N_samples, u=u, bins_in=bins, want_samples=True,
-                                      seed=int(getattr(opts, 'seed', 0)), offset=_next_offset(n * N_samples // 4 + 1))
+                                      seed=int(getattr(opts, 'seed', 0)), offset=_next_offset(n * N_samples // 4 + 1),
+                                      cdf_rows=-1 if getattr(opts, 'cdf_order', 'cuda') == 'fp64' else n)
     return samples
 
 

@@ -48,8 +48,9 @@ def import_reference():
     rp = importlib.util.module_from_spec(spec)   # dataset/__init__ pulls matplotlib/imageio (absent): load the file directly
     spec.loader.exec_module(rp)
     get_render_pose = rp.get_render_pose
+    import scheduler as ref_sched
     return SimpleNamespace(rays=ref_rays, proc=ref_np, NeRF=RefNeRF, posenc=ref_posenc,
-                           get_render_pose=get_render_pose)
+                           get_render_pose=get_render_pose, scheduler=ref_sched)
 
 
 class Recorder:
@@ -105,6 +106,105 @@ def state_to_np(module):
     return {k: v.detach().numpy().copy() for k, v in module.state_dict().items()}
 
 
+def gen_render_train_w256(ref, rec):
+    """The BENCHMARKED configuration pinned on the reference: full-width NeRF(8,256,63,27,[4]) at its seed-0
+    PLAIN random init (and a variant with linear_density.weight x30 so that densities are not ~0), 1024 rays of an 800x800
+    Blender-shaped view, 64+128 samples, perturb=1 with the draws recorded, MSE_c + MSE_f, backward.  Stores the render, the
+    per-sample densities the two networks produced (for the last-sample sign-decision count, nerf_process.py:98), the losses and
+    the WHOLE gradient vector of both networks.  Weights are not stored: they are the seed-0 init (param checksums are)."""
+    H8 = W8 = 800
+    K8 = blender_K(H8, W8)
+    poses = ref.get_render_pose(n_angle=120, single_angle=-1, phi=-30.0, nf=4.0).numpy()
+    pose8 = torch.from_numpy(poses[33][:3, :4].copy())
+    o8, d8 = ref.rays.make_o_d(W8, H8, torch.from_numpy(K8), pose8)
+    fx, _ = ref.posenc(10)
+    fd, _ = ref.posenc(4)
+    opts = SimpleNamespace(near=2., far=6., gpu_ids=[0], rank=0, N_samples_c=64, N_samples_f=128,
+                           perturb=1., chunk_pts=524288, chunk_rays=4096, data_type='blender')
+    N = 1024
+    sel = np.random.RandomState(6).choice(H8 * W8, N, replace=False).astype(np.int64)
+    ro, rd_ = o8.reshape(-1, 3)[sel].contiguous(), d8.reshape(-1, 3)[sel].contiguous()
+    target = torch.rand(N, 3, generator=torch.Generator().manual_seed(7))
+    for tag, scale in (('plain', 1.0), ('dens30', 30.0)):
+        torch.manual_seed(0)
+        net = ref.NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None))
+        sd0 = net.state_dict()
+        sums = np.array([float(v.double().sum()) for v in sd0.values()])
+        if scale != 1.0:
+            with torch.no_grad():
+                for m in (net.model_coarse, net.model_fine):
+                    m.linear_density.weight.mul_(scale)
+        raws = []
+        hooks = [m.register_forward_hook(lambda mod, inp, out: raws.append(out.detach().clone()))
+                 for m in (net.model_coarse, net.model_fine)]
+        torch.manual_seed(100)
+        rec.rand.clear()
+        net.zero_grad()
+        rgb_c, disp_c, rgb_f, disp_f = ref.proc.batchify_rays_and_render_by_chunk(ro, rd_, net, [fx, fd], H8, W8, torch.from_numpy(K8), opts)
+        for h in hooks:
+            h.remove()
+        t_rand, u = rec.rand[0], rec.rand[1]
+        assert len(raws) == 2 and raws[0].shape == (N * 64, 4) and raws[1].shape == (N * 192, 4)
+        crit = torch.nn.MSELoss()
+        loss_c, loss_f = crit(rgb_c, target), crit(rgb_f, target)
+        (loss_c + loss_f).backward()
+        gc = torch.cat([p.grad.reshape(-1) for p in net.model_coarse.parameters()]).numpy()
+        gf = torch.cat([p.grad.reshape(-1) for p in net.model_fine.parameters()]).numpy()
+        np.savez_compressed(os.path.join(OUT, f'render_train_w256_{tag}.npz'), rays_o=ro.numpy(), rays_d=rd_.numpy(), target=target.numpy(),
+                            t_rand=t_rand.numpy(), u=u.numpy(), near=2., far=6., density_scale=scale,
+                            rgb_c=rgb_c.detach().numpy(), disp_c=disp_c.detach().numpy(), rgb_f=rgb_f.detach().numpy(),
+                            disp_f=disp_f.detach().numpy(), loss_c=float(loss_c), loss_f=float(loss_f),
+                            sigma_c=raws[0][:, 3].reshape(N, 64).numpy(), sigma_f=raws[1][:, 3].reshape(N, 192).numpy(),
+                            grad_coarse=gc, grad_fine=gf, param_sums_seed0=sums, param_names=np.array(list(sd0.keys())))
+
+
+def gen_checkpoint(ref, rec):
+    """A checkpoint WRITTEN BY THE REFERENCE's own code path (train.py:105-114: {'idx', 'model_state_dict', 'optimizer_state_dict'}
+    of the reference NeRF module and torch.optim.Adam after 3 real reference train steps; small W=64 net so the file stays small),
+    plus what the reference computes when it RESUMES from it (main.py:111-117) and takes one more step on recorded inputs."""
+    H8 = W8 = 800
+    K8 = blender_K(H8, W8)
+    poses = ref.get_render_pose(n_angle=120, single_angle=-1, phi=-30.0, nf=4.0).numpy()
+    o8, d8 = ref.rays.make_o_d(W8, H8, torch.from_numpy(K8), torch.from_numpy(poses[5][:3, :4].copy()))
+    fx, _ = ref.posenc(10)
+    fd, _ = ref.posenc(4)
+    opts = SimpleNamespace(near=2., far=6., gpu_ids=[0], rank=0, N_samples_c=64, N_samples_f=128,
+                           perturb=1., chunk_pts=524288, chunk_rays=4096, data_type='blender')
+    N = 64
+    torch.manual_seed(3)
+    net = ref.NeRF(8, 64, 63, 27, [4], gt_camera_param=(None, None))
+    with torch.no_grad():
+        for m in (net.model_coarse, net.model_fine):
+            m.linear_density.weight.mul_(30.)
+    opt = torch.optim.Adam(net.parameters(), lr=5e-4, betas=(0.9, 0.999))                    # main.py:79-80
+    sched = ref.scheduler.CosineAnnealingWarmupRestarts(opt, first_cycle_steps=1000, cycle_mult=1., max_lr=5e-4, min_lr=5e-5,
+                                                        warmup_steps=10) if hasattr(ref, 'scheduler') else None
+    crit = torch.nn.MSELoss()
+
+    def step(i):
+        sel = np.random.RandomState(50 + i).choice(H8 * W8, N, replace=False)
+        ro, rd_ = o8.reshape(-1, 3)[sel].contiguous(), d8.reshape(-1, 3)[sel].contiguous()
+        target = torch.rand(N, 3, generator=torch.Generator().manual_seed(60 + i))
+        rec.rand.clear()
+        rgb_c, _, rgb_f, _ = ref.proc.batchify_rays_and_render_by_chunk(ro, rd_, net, [fx, fd], H8, W8, torch.from_numpy(K8), opts)
+        opt.zero_grad()
+        loss = crit(rgb_c, target) + crit(rgb_f, target)
+        loss.backward()
+        opt.step()
+        if sched is not None:
+            sched.step()
+        return dict(rays_o=ro.numpy(), rays_d=rd_.numpy(), target=target.numpy(), t_rand=rec.rand[0].numpy(), u=rec.rand[1].numpy(),
+                    loss=float(loss), lr=float(opt.param_groups[0]['lr']))
+    for i in range(3):
+        step(i)
+    ckpt = {'idx': 3, 'model_state_dict': net.state_dict(), 'optimizer_state_dict': opt.state_dict()}      # train.py:107-109
+    torch.save(ckpt, os.path.join(OUT, 'ref_checkpoint_w64_3.pth.tar'))
+    lr_resume = float(opt.param_groups[0]['lr'])
+    rec4 = step(3)                                                                                         # the resumed step
+    np.savez_compressed(os.path.join(OUT, 'ref_checkpoint_w64_resume.npz'), lr_resume=lr_resume,
+                        **{'in/' + k: v for k, v in rec4.items()}, **{'a/' + k: v for k, v in state_to_np(net).items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = import_reference()
@@ -113,7 +213,17 @@ def main():
     patches = cpu_patches(rec)
     for p in patches:
         p.start()
+    only = [a for a in sys.argv[1:] if not a.startswith('-')]
     try:
+        torch.set_num_threads(8)
+        if only:                       # e.g. `python oracle/make_golden.py w256 ckpt`: regenerate just these fixtures
+            if 'w256' in only:
+                gen_render_train_w256(ref, rec)
+            if 'ckpt' in only:
+                gen_checkpoint(ref, rec)
+            return
+        gen_render_train_w256(ref, rec)
+        gen_checkpoint(ref, rec)
         torch.manual_seed(0)
         np.random.seed(0)
         torch.set_num_threads(8)

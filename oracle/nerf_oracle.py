@@ -167,15 +167,91 @@ def stratified_z(near, far, n_samples, t_rand, t_vals=None):
     return (lower[None, :] + (upper - lower)[None, :] * t_rand).astype(np.float32)
 
 
-def pdf_to_cdf(weights):
+def aten_cuda_scan_threads_x(num_rows, row_size):
+    """ATen ScanUtils.cuh get_log_num_threads_x_inner_scan<uint32_t> (torch 2.x): threads per row of the innermost-dim scan
+    kernel, INCLUDING its unsigned wrap-around when num_rows >> row_size."""
+    lx = ly = 0
+    while (1 << lx) < row_size:
+        lx += 1
+    while (1 << ly) < num_rows:
+        ly += 1
+    diff = (lx - ly) & 0xFFFFFFFF
+    lx = ((9 + diff) & 0xFFFFFFFF) // 2
+    return 1 << min(max(4, lx), 9)
+
+
+def aten_cuda_sum_lastdim(w):
+    """torch.sum(w, -1, keepdim=True) of a contiguous fp32 [N, n] tensor on CUDA for n < 128 (ATen Reduce.cuh, no input
+    vectorisation): block_width bw = min(2^floor(log2 n), 32) lanes; lane x owns elements x, x+bw, x+2bw, x+3bw in four
+    accumulators combined as ((v0+v1)+v2)+v3; then block_x_reduce: p[x] += p[x+off] for off = bw/2 .. 1."""
+    w = _f32(w)
+    n = w.shape[-1]
+    assert 1 <= n < 128
+    bw = 1
+    while bw * 2 <= n and bw < 32:
+        bw *= 2
+    pad = np.zeros(w.shape[:-1] + (4 * bw,), np.float32)
+    pad[..., :n] = w
+    v = pad.reshape(w.shape[:-1] + (4, bw))
+    p = (((v[..., 0, :] + v[..., 1, :]).astype(np.float32) + v[..., 2, :]).astype(np.float32) + v[..., 3, :]).astype(np.float32)
+    off = bw // 2
+    while off > 0:
+        p = p.copy()
+        p[..., :off] = (p[..., :off] + p[..., off:2 * off]).astype(np.float32)
+        off //= 2
+    return p[..., :1]
+
+
+def aten_cuda_cumsum_lastdim(x, num_rows=None):
+    """torch.cumsum(x, -1) of a contiguous fp32 [N, n] tensor on CUDA (ATen ScanUtils.cuh tensor_kernel_scan_innermost_dim):
+    Sklansky scan over blocks of 2*ntx elements, the running total added to the first element of the next block."""
+    x = _f32(x)
+    N, n = x.shape
+    ntx = aten_cuda_scan_threads_x(N if num_rows is None else num_rows, n)
+    B = 2 * ntx
+    out = np.empty_like(x)
+    total = np.zeros(N, np.float32)
+    lg = ntx.bit_length() - 1
+    for c0 in range(0, n, B):
+        m_len = min(B, n - c0)
+        width = 1
+        while width < m_len:
+            width *= 2
+        buf = np.zeros((N, max(width, 2)), np.float32)          # elements past the block end never feed kept outputs
+        buf[:, :m_len] = x[:, c0:c0 + m_len]
+        buf[:, 0] = (buf[:, 0] + total).astype(np.float32)
+        for mm in range(lg + 1):
+            sft = 1 << mm
+            if sft >= buf.shape[1]:
+                break
+            new = buf.copy()
+            for t in range(min(ntx, buf.shape[1] // 2)):
+                a = ((t >> mm) << (mm + 1)) | sft
+                ti = a + (t % sft)
+                if ti < buf.shape[1]:
+                    new[:, ti] = (buf[:, ti] + buf[:, a - 1]).astype(np.float32)
+            buf = new
+        out[:, c0:c0 + m_len] = buf[:, :m_len]
+        if m_len == B:
+            total = buf[:, B - 1].copy()
+    return out
+
+
+def pdf_to_cdf(weights, order='cpu', rows=None):
     """nerf_process.py:150-155.  weights[N,M] (already sliced [...,1:-1]) -> cdf[N,M+1].
 
-    Summation order is device specific in the reference (SURVEY B-5).  The
-    oracle (and the CUDA kernel) define it as: row sum accumulated in float64
-    then rounded to fp32; cumsum accumulated in float64, each output rounded to
-    fp32 (the latter is exactly ATen's CPU cumsum).
+    Summation order is device specific in the reference (SURVEY B-5):
+      order='cpu'  : row sum accumulated in float64 then rounded to fp32; cumsum accumulated in float64, each output rounded
+                     to fp32 (the latter is exactly ATen's CPU cumsum) -- the order the CPU-generated fixtures are closest to;
+      order='cuda' : the exact fp32 order of torch.sum / torch.cumsum on CUDA for a call with `rows` rows (default N), pinned
+                     bit for bit against the reference running on a B200 (tests/golden/sample_pdf_cuda.npz).
     """
     w = (_f32(weights) + F32(1e-5)).astype(np.float32)
+    if order == 'cuda':
+        s = aten_cuda_sum_lastdim(w)
+        pdf = (w / s).astype(np.float32)
+        cdf = aten_cuda_cumsum_lastdim(pdf, rows)
+        return np.concatenate([np.zeros_like(cdf[..., :1]), cdf], -1)
     s = w.astype(np.float64).sum(-1, keepdims=True).astype(np.float32)
     pdf = (w / s).astype(np.float32)
     cdf = np.cumsum(pdf.astype(np.float64), -1).astype(np.float32)
@@ -205,18 +281,18 @@ def invert_cdf(bins, cdf, u):
     return samples.astype(np.float32), inds
 
 
-def sample_pdf(bins, weights, u):
+def sample_pdf(bins, weights, u, order='cpu', rows=None):
     """nerf_process.py:144-182 with u injected (det: torch.linspace(0,1,S_f) expanded)."""
-    cdf = pdf_to_cdf(weights)
+    cdf = pdf_to_cdf(weights, order, rows)
     u = np.broadcast_to(_f32(u), (cdf.shape[0], np.shape(u)[-1]))
     return invert_cdf(bins, cdf, u)
 
 
-def fine_z(z_vals, weights, u):
+def fine_z(z_vals, weights, u, order='cpu', rows=None):
     """nerf_process.py:62-67.  mids -> sample_pdf(weights[...,1:-1]) -> sort(cat)."""
     z_vals = _f32(z_vals)
     mids = F32(.5) * (z_vals[..., 1:] + z_vals[..., :-1])
-    z_samples, inds = sample_pdf(mids, _f32(weights)[..., 1:-1], u)
+    z_samples, inds = sample_pdf(mids, _f32(weights)[..., 1:-1], u, order, rows)
     z_fine = np.sort(np.concatenate([z_vals, z_samples], -1), -1)
     return z_fine.astype(np.float32), z_samples, inds
 

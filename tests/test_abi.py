@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     assert len(fns) >= 25
     for name in fns:
         assert hasattr(lib, name), f'{name} declared in nerf_b200.h but not exported'
-    assert lib.nb_abi_version() == 1
+    assert lib.nb_abi_version() == 2
 
 
 def test_ctypes_table_matches_header():

@@ -26,7 +26,7 @@ def npy(t):
 def make_opts(**kw):
     base = dict(near=2., far=6., N_samples_c=64, N_samples_f=128, perturb=1., data_type='blender', gpu_ids=[0], rank=0,
                 chunk_rays=4096, chunk_pts=524288, N_rays=1024, precrop_iters=0, precrop_frac=.5, seed=0, global_batch=False,
-                idx_print=10 ** 9, idx_save=None, exp_name='t')
+                idx_print=10 ** 9, idx_save=None, exp_name='t', cdf_order='fp64')    # fixtures / oracle: CPU summation order
     base.update(kw)
     return SimpleNamespace(**base)
 

@@ -32,7 +32,7 @@ def npy(t):
 
 def make_opts(**kw):
     base = dict(near=2., far=6., N_samples_c=64, N_samples_f=128, perturb=1., data_type='blender', gpu_ids=[0], rank=0,
-                chunk_rays=4096, chunk_pts=524288, N_rays=4096, precrop_iters=0, precrop_frac=.5, seed=0)
+                chunk_rays=4096, chunk_pts=524288, N_rays=4096, precrop_iters=0, precrop_frac=.5, seed=0, cdf_order='fp64')    # fixtures / oracle: CPU summation order
     base.update(kw)
     return SimpleNamespace(**base)
 
@@ -188,7 +188,7 @@ def test_sample_pdf_bit_exact(eng):
     # (2) own cdf (fp64 accumulation): bit-exact against the oracle, which defines the same order
     for tag in ('det', 'rnd'):
         u = cu(g[f'u_{tag}'])
-        z_f, zs, inds, cdf = eng.sample_pdf(z, w, 128, u=u, want_samples=True, want_inds=True, want_cdf=True)
+        z_f, zs, inds, cdf = eng.sample_pdf(z, w, 128, u=u, want_samples=True, want_inds=True, want_cdf=True, cdf_rows=-1)
         o_cdf = orc.pdf_to_cdf(g['weights'][..., 1:-1])
         assert np.array_equal(npy(cdf), o_cdf)
         o_zf, o_zs, o_inds = orc.fine_z(g['z_vals'], g['weights'], g[f'u_{tag}'])
@@ -207,7 +207,7 @@ def test_sample_pdf_bit_exact(eng):
         zz = torch.sort(torch.rand(3, sc, device='cuda') * 4 + 2, -1)[0]
         ww = torch.rand(3, sc, device='cuda')
         uu = torch.rand(3, sf, device='cuda')
-        z_f, _, inds, _ = eng.sample_pdf(zz, ww, sf, u=uu, want_inds=True)
+        z_f, _, inds, _ = eng.sample_pdf(zz, ww, sf, u=uu, want_inds=True, cdf_rows=-1)
         o_zf, _, o_inds = orc.fine_z(npy(zz), npy(ww), npy(uu))
         assert np.array_equal(npy(inds), o_inds) and np.array_equal(npy(z_f), o_zf)
 

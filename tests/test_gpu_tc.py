@@ -167,10 +167,15 @@ def decode_blobs(buf, off, tiles, nblk):
 
 
 def decode_masks(buf, off, tiles):
-    """[tiles][9][128][8 x u32] -> bool "active" [9, tiles*128, 256]; bit (31-j) of word c is the SIGN of column 32c+j."""
-    w = buf[off:off + tiles * 9 * 128 * 32].view(np.uint32).reshape(tiles, 9, 128, 8)
-    bits = (((w[..., None] >> (31 - np.arange(32, dtype=np.uint32))) & 1) == 0).reshape(tiles, 9, 128, 256)
-    return bits.transpose(1, 0, 2, 3).reshape(9, tiles * 128, 256)
+    """[tiles][9][2 column halves][128][4 x u32] -> bool "active" [9, tiles*128, 256]; bit (31-j) of word w of half h is the SIGN of
+    column 128h+32w+j (layer 8 = g, 128 wide: column 64h+32w+j, words 2,3 unused)."""
+    w = buf[off:off + tiles * 9 * 128 * 32].view(np.uint32).reshape(tiles, 9, 2, 128, 4)
+    bits = (((w[..., None] >> (31 - np.arange(32, dtype=np.uint32))) & 1) == 0)          # [tiles, 9, 2, 128, 4, 32]
+    full = bits.transpose(0, 1, 3, 2, 4, 5).reshape(tiles, 9, 128, 256)
+    g = bits[:, 8, :, :, :2, :].transpose(0, 2, 1, 3, 4).reshape(tiles, 128, 128)
+    full[:, 8, :, :128] = g
+    full[:, 8, :, 128:] = True
+    return full.transpose(1, 0, 2, 3).reshape(9, tiles * 128, 256)
 
 
 def stash_offsets(tiles):

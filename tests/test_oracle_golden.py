@@ -184,3 +184,43 @@ def test_lr_schedule():
     assert abs(orc.lr_at(10000) - 5e-4) < 1e-12
     assert abs(orc.lr_at(5000) - (5e-5 + 4.5e-4 * 0.5)) < 1e-12
     assert orc.lr_at(200000) < 5.1e-5
+
+
+def _seed0_params_w256(scale):
+    """The seed-0 init of the full-width network, built with the product's host-side module (same RNG consumption as the
+    reference's constructor; verified against the fixture's parameter checksums below)."""
+    import torch
+    from nerf_pytorch_paeng_b200.model import NeRF
+    torch.manual_seed(0)
+    net = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None))
+    sd = {k: v.detach().numpy().copy() for k, v in net.state_dict().items()}
+    out = {'coarse': {}, 'fine': {}}
+    for k, v in sd.items():
+        net_name, rest = k.split('.', 1)
+        out[net_name.replace('model_', '')][rest] = v * np.float32(scale) if rest == 'linear_density.weight' else v
+    return sd, out
+
+
+@pytest.mark.parametrize('tag', ['plain', 'dens30'])
+def test_render_train_w256_random_init(tag):
+    """The benchmarked configuration (full-width net at its PLAIN seed-0 random init, and the density x30 variant; 1024 rays,
+    64+128) pinned on the unmodified reference: render, per-sample densities, losses and the whole gradient vectors."""
+    g = load_golden(f'render_train_w256_{tag}.npz')
+    sd, p = _seed0_params_w256(float(g['density_scale']))
+    sums = np.array([float(v.astype(np.float64).sum()) for v in sd.values()])
+    assert list(sd.keys()) == [str(s) for s in g['param_names']]
+    assert np.abs(sums - g['param_sums_seed0']).max() <= 1e-9 * max(1., np.abs(sums).max())      # same seed-0 weights as the reference
+    opts = orc.make_opts(near=float(g['near']), far=float(g['far']))
+    rays = np.concatenate([g['rays_o'], g['rays_d']], -1)
+    r = orc.render_rays(rays, p['coarse'], p['fine'], opts, g['t_rand'], g['u'])
+    # two fp32 implementations (numpy/OpenBLAS vs torch/MKL): a ray whose LAST sample has |sigma| ~ 1e-8 can land on either side of
+    # the 1e10-interval step of nerf_process.py:98; count them instead of hiding them
+    for k in ('rgb_c', 'rgb_f'):
+        e = np.abs(r[k] - g[k]).max(-1)
+        assert (e > 1e-4).sum() <= 2, (k, (e > 1e-4).sum(), e.max())
+    lc, lf, gc, gf = orc.train_grads(rays, g['target'], p['coarse'], p['fine'], opts, g['t_rand'], g['u'])
+    assert abs(lc - float(g['loss_c'])) <= 1e-4 and abs(lf - float(g['loss_f'])) <= 1e-4
+    for tag_n, grads, ref in (('coarse', gc, g['grad_coarse']), ('fine', gf, g['grad_fine'])):
+        flat = np.concatenate([grads[k].reshape(-1) for k in orc.mlp_param_names()])
+        rel = np.linalg.norm((flat - ref).astype(np.float64)) / np.linalg.norm(ref.astype(np.float64))
+        assert rel <= 2e-3, (tag_n, rel)
