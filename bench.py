@@ -6,10 +6,17 @@
 One "step" = one full train step (ray batch -> coarse+fine render -> MSE_c+MSE_f -> backward ->
 Adam) on 4096 rays PER GPU (weak scaling) of the Blender-lego-shaped synthetic workload
 (BASELINE.json configs[1]).  Prints ONE JSON line (rank 0).  `value` times the step with the ray
-batch already resident in HBM; `e2e` times the reference-facing call train.train(...) with the
-target image and pixel indices coming from pinned HOST memory every step and the loss read back.
-`--impl reference` times the CPU restatement of the reference (oracle/, numpy+BLAS on all host
-cores) on a bounded sample of the same workload; under torchrun only rank 0 runs it.
+batch already resident in HBM; `e2e` times the reference-facing call train.train(...) driven from
+the host every step (camera pose from pinned host memory, on-device pixel selection + ray
+generation + target gather from the device-resident image stack, loss copied back to the host).
+The line also carries `roofline` (tensor pipe of the MLP kernels, HBM figures beside it),
+`cpu_baseline` (the UNMODIFIED reference, baseline/_ref, on this box's host cores: BASELINE
+configs[0], 1024 rays) and `gpu_baseline` (the unmodified reference's own eager-PyTorch CUDA path on
+this GPU: the like-for-like figure); for N > 1 `dp_check` (sum of the rank gradients against the
+single-GPU gradient of the concatenated batch) and `strong_scaling` (4096/N rays per GPU).
+`--impl reference` times the reference's CPU path (all host threads, thread count set explicitly
+because torchrun exports OMP_NUM_THREADS=1) on a bounded sample of the workload; under torchrun
+only rank 0 runs it.  oracle/ is used only as the fallback CPU port when baseline/_ref is absent.
 """
 import argparse
 import json
@@ -151,24 +158,40 @@ def cpu_port_step(n_rays, seed=0):
     return time.perf_counter() - t0
 
 
+def cpu_reference(n_rays, steps, warmup):
+    """CPU baseline on this box: the unmodified reference (kind 'reference') when baseline/_ref travelled here, else the numpy
+    port in oracle/ (kind 'port').  Returns the cpu_baseline object (value = train rays/s)."""
+    from baseline import ref_shim
+    cores = os.cpu_count()
+    if ref_shim.available():
+        from baseline import ref_bench
+        r = ref_bench.time_cpu(n_rays=n_rays, steps=steps, warmup=warmup, threads=cores)
+        return {'value': r['train_rays_per_s'], 'unit': 'rays/s', 'cores': r['threads'], 'kind': 'reference',
+                'sample': f'{n_rays}-ray train step (make_o_d + sample_rays_and_pixel + render 64+128 + MSE_c+MSE_f + backward + Adam) of the '
+                          f'unmodified reference on CPU, mean of {steps} after {warmup} warm-up (BASELINE configs[0] shape)',
+                'ms_per_step': r['train_ms_per_step'], 'render_rays_per_s': r['render_rays_per_s'], 'cpu_count': r['cpu_count'],
+                'cpu_model': r['cpu_model'], 'torch_threads': r['threads']}
+    for _ in range(max(1, warmup)):
+        cpu_port_step(min(n_rays, 256))
+    ts = [cpu_port_step(min(n_rays, 256), seed=i + 1) for i in range(max(1, steps))]
+    return {'value': min(n_rays, 256) / float(np.mean(ts)), 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+            'sample': f'{min(n_rays, 256)}-ray train step of oracle/nerf_oracle.py (numpy/BLAS); baseline/_ref not installed',
+            'ms_per_step': 1e3 * float(np.mean(ts))}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n = args.cpu_rays
-    for _ in range(max(1, min(args.warmup, 2))):
-        cpu_port_step(n)
-    times = [cpu_port_step(n, seed=i + 1) for i in range(max(1, min(args.steps, 5)))]
-    ms = 1e3 * float(np.mean(times))
-    val = n / (ms / 1e3)
-    cores = os.cpu_count()
-    line = {'impl': 'reference', 'metric': 'train_rays_per_s', 'value': val, 'unit': 'rays/s', 'n_gpus': args.gpus,
-            'steps': len(times), 'warmup': max(1, min(args.warmup, 2)), 'ms_per_step': ms, 'higher_is_better': True,
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 2))
+    cpu = cpu_reference(args.cpu_rays, steps, warmup)
+    line = {'impl': 'reference', 'metric': 'train_rays_per_s', 'value': cpu['value'], 'unit': 'rays/s', 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': warmup, 'ms_per_step': cpu['ms_per_step'], 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'sample': f'{n} rays per step (bounded sample of the 4096-ray batch)'},
-            'cpu_baseline': {'value': val, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
-                             'sample': f'{n}-ray train step (render+grads+Adam) of oracle/nerf_oracle.py, numpy/BLAS threads={cores}'},
-            'e2e': {'value': val, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'config': {'workload': WORKLOAD, 'sample': f'{args.cpu_rays} rays per step (bounded sample of the 4096-ray batch; the reference\'s CPU path, '
+                                                       'a reported baseline: the like-for-like GPU figure is gpu_baseline of the other arm)'},
+            'cpu_baseline': cpu,
+            'e2e': {'value': cpu['value'], 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     emit(line)
 
@@ -289,59 +312,136 @@ def run_ours(args):
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
+    tsrc = traffic.get('source', 'profiles/traffic.json (ncu --set full dram__bytes of an earlier run of this command; not measured in this run)')
     flop_step = FLOP_PER_POINT_TRAIN * N_RAYS * POINTS_PER_RAY
     fwd_tf = FLOP_PER_POINT_FWD * pts_per_launch / (avg['fwd'] / 1e3) / 1e12
-    # wgrad: algorithmic HBM bytes = every 16 KB operand blob its 12 jobs read: 85 blobs per 128-point tile
+    # wgrad's algorithmic HBM bytes: every 16 KB operand blob its 12 jobs read: 85 blobs per 128-point tile
     WGRAD_BYTES_PER_POINT = 85 * 16384 / 128.0
     other = {'mlp_fwd_chain_kernel<train>': {'bound': 'tensor', 'achieved': fwd_tf, 'unit': 'TFLOP/s', 'frac': fwd_tf / peak_tf,
                                              'avg_launch_ms': avg['fwd'], 'traffic': traffic.get('mlp_fwd_chain_kernel_bytes_per_launch')}}
     if args.precision == 'bf16':
         wg_gbs = WGRAD_BYTES_PER_POINT * pts_per_launch / (avg['wgrad'] / 1e3) / 1e9
-        dg_tf = 1115392 * pts_per_launch / (avg['dgrad'] / 1e3) / 1e12       # dgrad: 557,696 MAC per point
+        wg_tf = FLOP_PER_POINT_FWD * pts_per_launch / (avg['wgrad'] / 1e3) / 1e12    # dW = dY^T X: the forward's 593,408 MAC per point
+        dg_tf = 1115392 * pts_per_launch / (avg['dgrad'] / 1e3) / 1e12               # dgrad: 557,696 MAC per point
         other['mlp_dgrad_chain_kernel'] = {'bound': 'tensor', 'achieved': dg_tf, 'unit': 'TFLOP/s', 'frac': dg_tf / peak_tf,
                                            'avg_launch_ms': avg['dgrad'], 'traffic': traffic.get('mlp_dgrad_chain_kernel_bytes_per_launch')}
-        roofline = {'bound': 'hbm', 'achieved': wg_gbs, 'peak': peak_hbm, 'unit': 'GB/s', 'frac': wg_gbs / peak_hbm,
-                    'traffic': traffic.get('mlp_wgrad_kernel_bytes_per_launch'),
+        other['mlp_wgrad_kernel as an HBM stream'] = {
+            'bound': 'hbm', 'achieved': wg_gbs, 'peak': peak_hbm, 'unit': 'GB/s', 'frac': wg_gbs / peak_hbm,
+            'algorithmic_bytes_per_launch': WGRAD_BYTES_PER_POINT * pts_per_launch,
+            'note': 'the kernel streams 10.9 KB/point of stashed operands; this is the roofline that binds it in practice (DESIGN.md section 4)'}
+        # headline: the dominant kernel by time share (profiles/*launches*.csv) against SURVEY 8(d)'s bound for K4, the tensor pipe
+        roofline = {'bound': 'tensor', 'achieved': wg_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': wg_tf / peak_tf,
+                    'traffic': traffic.get('mlp_wgrad_kernel_bytes_per_launch'), 'traffic_source': tsrc,
                     'kernel': 'mlp_wgrad_kernel (tcgen05 weight-gradient GEMMs, MN-major operands streamed from the activation stash)',
-                    'algorithmic_bytes_per_launch': WGRAD_BYTES_PER_POINT * pts_per_launch, 'avg_launch_ms': avg['wgrad'],
-                    'launches_per_step': 2, 'peak_source': peak_src.replace('sustained bf16', 'hbm_gbs')}
+                    'algorithmic_flop_per_launch': FLOP_PER_POINT_FWD * pts_per_launch, 'avg_launch_ms': avg['wgrad'],
+                    'launches_per_step': 2, 'peak_source': peak_src}
     else:
         roofline = dict(other.pop('mlp_fwd_chain_kernel<train>'), peak=peak_tf, kernel='sgemm_kernel chain (fp32 CUDA-core parity path)',
                         peak_source=peak_src)
     roofline['other_kernels'] = other
     roofline['whole_step'] = {'algorithmic_flop_per_step': flop_step, 'mlp_ms_per_step': mlp_ms, 'mlp_share_of_step': mlp_ms / ms_step,
-                              'achieved_tflops': flop_step / (mlp_ms / 1e3) / 1e12, 'frac_of_bf16_peak': flop_step / (mlp_ms / 1e3) / 1e12 / peak_tf}
+                              'achieved_tflops': flop_step / (mlp_ms / 1e3) / 1e12, 'frac_of_bf16_peak': flop_step / (mlp_ms / 1e3) / 1e12 / peak_tf,
+                              'whole_step_incl_everything_tflops': flop_step / (ms_step / 1e3) / 1e12,
+                              'whole_step_frac_of_bf16_peak': flop_step / (ms_step / 1e3) / 1e12 / peak_tf}
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- e2e: the reference-facing call train.train(...) with HOST inputs every step
+    # ---- e2e: the reference-facing call train.train(...) driven from the host every step.  The training images are a
+    # device-resident stack (uploaded once); what crosses PCIe per step is the selected camera pose (pinned host
+    # memory -> device) and the step's loss (device -> pinned host memory, consumed two steps later so that the host never
+    # blocks the queue).  `per_step_image_upload` repeats the measurement with the reference's own behaviour (train.py:37-38:
+    # the whole 7.68 MB image uploaded every step) for comparison.
     n_img = 4
     images = [torch.rand(H, W, 3).pin_memory() for _ in range(n_img)]
-    gt_cam = (K, poses[:n_img])
+    poses_pin = torch.from_numpy(poses[:n_img]).pin_memory()
+    gt_cam = (K, poses_pin)
     crit = torch.nn.MSELoss()
     np.random.seed(rank)
-    host_loss = torch.zeros(1).pin_memory()
+    host_loss = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_ev = [None, None]
 
-    def e2e_step(i):
-        loss = train_mod.train(i + 1, list(range(n_img)), images, gt_cam, (H, W), model, crit, posenc, optimizer, None, None, opts,
-                               dist_ctx=dctx)
-        host_loss.copy_(loss.reshape(1), non_blocking=False)      # D2H read of the step's result
-        return float(host_loss)
-    for i in range(max(3, args.warmup // 2)):
-        e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(i)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([e2e_ms], device=dev)
-    if dctx:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    e2e_ms_step = float(t) / args.steps
+    def run_e2e(cache_images):
+        opts.cache_images, opts.cache_poses = cache_images, False
+        seen = []
+
+        def e2e_step(i):
+            slot = i % 2
+            if loss_ev[slot] is not None:
+                loss_ev[slot].synchronize()
+                seen.append(float(host_loss[slot]))                    # the loss of step i-2, read on the host
+            loss = train_mod.train(i + 1, list(range(n_img)), images, gt_cam, (H, W), model, crit, posenc, optimizer, None, None, opts,
+                                   dist_ctx=dctx)
+            host_loss[slot].copy_(loss.detach().reshape(1), non_blocking=True)   # D2H read of the step's result
+            loss_ev[slot] = torch.cuda.Event()
+            loss_ev[slot].record()
+        for i in range(max(4, args.warmup)):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(i)
+        barrier()
+        ms = (time.perf_counter() - t0) * 1e3
+        tt = torch.tensor([ms], device=dev)
+        if dctx:
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        assert len(seen) >= args.steps and np.isfinite(seen).all()
+        return float(tt) / args.steps
+    e2e_ms_step = run_e2e(True)
+    e2e_upload_ms = run_e2e(False)
+    opts.cache_images = opts.cache_poses = True
     e2e = {'value': N_RAYS * world / (e2e_ms_step / 1e3), 'unit': 'rays/s', 'ms_per_step': e2e_ms_step,
-           'h2d_bytes_per_step': H * W * 3 * 4, 'd2h_bytes_per_step': 4,
-           'api': 'nerf_pytorch_paeng_b200.train.train (per-image path, train.py:35-45: pinned host image -> H2D every step, '
-                  'pixel selection + ray-gen + target gather + fused step + Adam on device, loss D2H)'}
+           'h2d_bytes_per_step': 48, 'd2h_bytes_per_step': 4,
+           'api': 'nerf_pytorch_paeng_b200.train.train (per-image path, train.py:35-45): pose from pinned host memory every step, on-device '
+                  'pixel selection + ray-gen + target gather from the device-resident image stack + fused step + Adam, loss D2H every step',
+           'per_step_image_upload': {'value': N_RAYS * world / (e2e_upload_ms / 1e3), 'ms_per_step': e2e_upload_ms,
+                                     'h2d_bytes_per_step': H * W * 3 * 4 + 48, 'note': 'opts.cache_images=False: the reference\'s per-step upload of the whole image'}}
+
+    # ---- N > 1: (a) the all-reduced gradient of a sharded batch against the single-GPU gradient of the concatenated batch
+    # (bf16 joint-buffer path, injected draws), (b) strong scaling: the same 4096 rays split over the ranks
+    dp_check = strong = None
+    if dctx is not None:
+        gg = torch.Generator(device='cpu').manual_seed(4242)
+        n_all = 1024 * world
+        pix_all = torch.randperm(H * W, generator=gg)[:n_all].to(dev)
+        o, d = eng.raygen(H, W, K, poses_dev[3, :3, :4], pix_idx=pix_all, ndc=llff, ndc_focal=float(K[0][0]), ndc_near=1.)
+        rays_all = torch.cat((o, d), -1)
+        tgt_all = torch.rand(n_all, 3, generator=gg).to(dev)
+        tr_all, u_all = torch.rand(n_all, S_C, generator=gg).to(dev), torch.rand(n_all, S_F, generator=gg).to(dev)
+        lo, hi = rank * 1024, (rank + 1) * 1024
+        from types import SimpleNamespace as NS
+        o_sh = NS(**{**vars(opts), 'rng': {'t_rand': tr_all[lo:hi].contiguous(), 'u': u_all[lo:hi].contiguous()}})
+        whole, lossv = dctx.joint_grad_buffer(model)
+        lossv.zero_()
+        trainer.render_losses_and_grads(model, rays_all[lo:hi].contiguous(), tgt_all[lo:hi].contiguous(), o_sh, n_global=n_all, loss_buf=lossv)
+        dctx.allreduce_(whole)
+        summed = whole.clone()
+        o_one = NS(**{**vars(opts), 'rng': {'t_rand': tr_all, 'u': u_all}})
+        lossv.zero_()
+        trainer.render_losses_and_grads(model, rays_all, tgt_all, o_one, n_global=n_all, loss_buf=lossv)     # every rank: the whole batch alone
+        torch.cuda.synchronize()
+        ng = whole.numel() - 2
+        nc = model.model_coarse.flat_params().numel()
+        rel = lambda a, b: float((a - b).norm() / b.norm())
+        dp_check = {'what': f'sum over {world} ranks of the gradients of 1024-ray shards (bf16, joint buffer, one all-reduce) vs the single-GPU '
+                            f'gradient of the concatenated {n_all}-ray batch, identical injected draws',
+                    'grad_rel_err_coarse': rel(summed[:nc], whole[:nc]), 'grad_rel_err_fine': rel(summed[nc:ng], whole[nc:ng]),
+                    'loss_abs_err': float((summed[ng:] - whole[ng:]).abs().max())}
+        # strong scaling: global batch stays 4096 rays
+        n_loc = N_RAYS // world
+        sring = [(r[rank * n_loc:(rank + 1) * n_loc].contiguous(), t[rank * n_loc:(rank + 1) * n_loc].contiguous()) for r, t in ring]
+        for i in range(3):
+            trainer.train_step(model, optimizer, *sring[i % n_ring], opts, dist_ctx=dctx)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(args.steps):
+            trainer.train_step(model, optimizer, *sring[i % n_ring], opts, dist_ctx=dctx)
+        s1.record()
+        barrier()
+        tt = torch.tensor([s0.elapsed_time(s1)], device=dev)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        sms = float(tt) / args.steps
+        strong = {'scaling': 'strong', 'global_rays': N_RAYS, 'rays_per_gpu': n_loc, 'ms_per_step': sms, 'value': N_RAYS / (sms / 1e3), 'unit': 'rays/s'}
 
     # ---- second half of BASELINE.json's metric: full 800x800 coarse+fine frames/s, pixel bands sharded over ranks
     render = None
@@ -367,22 +467,33 @@ def run_ours(args):
                   'includes': 'ray-gen, sampling, MLP x2, compositing, band all-gather, uint8 frame D2H'}
     if rank != 0:
         return
-    # ---- cpu baseline on this box's host cores (bounded sample)
-    cpu = None
-    if not args.no_cpu:
-        cpu_port_step(args.cpu_rays)
-        ts = [cpu_port_step(args.cpu_rays, seed=i + 1) for i in range(2)]
-        cpu = {'value': args.cpu_rays / float(np.mean(ts)), 'unit': 'rays/s', 'cores': os.cpu_count(), 'kind': 'port',
-               'sample': f'{args.cpu_rays}-ray train step (render+grads+Adam) of oracle/nerf_oracle.py, numpy/BLAS on all host cores'}
+    # ---- baselines measured on this box in the same run (rank 0, N = 1 only): the unmodified reference on the host cores
+    # (BASELINE configs[0]: 1024 rays) and its own eager-PyTorch CUDA path on this GPU (configs[1] train step, configs[2] render)
+    cpu = gpu_base = None
+    if not args.no_cpu and world == 1:
+        cpu = cpu_reference(args.cpu_rays, 3, 1)
+        from baseline import ref_shim
+        if ref_shim.available() and not llff:
+            from baseline import ref_bench
+            del ring
+            torch.cuda.empty_cache()
+            gb = ref_bench.time_gpu(dev, n_rays=N_RAYS, steps=8, warmup=2, render_frames=0 if args.no_render else 1)
+            gpu_base = {'value': gb['train_rays_per_s'], 'unit': 'rays/s', 'ms_per_step': gb['train_ms_per_step'], 'kind': 'reference',
+                        'what': 'the unmodified reference (baseline/_ref) on this GPU: PyTorch eager fp32, its own train step at 4096 rays '
+                                '(make_o_d of the full image + host pixel selection + render + backward + Adam), CUDA events, 8 steps after 2',
+                        'peak_mem_GB': gb['peak_mem_GB'], 'render_frames_per_s': gb.get('render_frames_per_s'),
+                        'speedup_value': value / gb['train_rays_per_s'], 'speedup_e2e': e2e['value'] / gb['train_rays_per_s'],
+                        'speedup_render': (render['frames_per_s'] / gb['render_frames_per_s']) if (render and gb.get('render_frames_per_s')) else None}
     line = {'metric': 'train_rays_per_s', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD_LLFF if llff else WORKLOAD, 'rays_per_gpu': N_RAYS, 'global_rays': N_RAYS * world, 'samples': [S_C, S_F],
                        'precision': args.precision, 'parallelism': f'ray-sharded data parallel x{world}, one NCCL all-reduce of 1,191,690 fp32 (gradients of both nets + the two losses)',
                        'l2': 'per-step working set (activation stash >= 5 GB) exceeds the 126 MB L2; ring of 8 distinct ray batches',
+                       'timed_region': f'{args.steps} steps = {ms_step * args.steps:.0f} ms; a sustained figure over 12,000 steps of the same step is in profiles/ (train_demo)',
                        'loss': float(loss.sum())},
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'render': render, 'gpu_launches': int(launches), 'clocks': clocks,
-            'gpu_launches_per_step': launches / args.steps}
+            'roofline': roofline, 'cpu_baseline': cpu, 'gpu_baseline': gpu_base, 'e2e': e2e, 'render': render, 'gpu_launches': int(launches),
+            'clocks': clocks, 'gpu_launches_per_step': launches / args.steps, 'dp_check': dp_check, 'strong_scaling': strong}
     emit(line)
 
 
@@ -412,7 +523,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', type=str, default=os.environ.get('NB_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
-    ap.add_argument('--cpu-rays', dest='cpu_rays', type=int, default=256)
+    ap.add_argument('--cpu-rays', dest='cpu_rays', type=int, default=1024, help='rays per CPU-baseline step (BASELINE configs[0]: 1024)')
     ap.add_argument('--no-cpu', dest='no_cpu', action='store_true')
     ap.add_argument('--no-render', dest='no_render', action='store_true')
     ap.add_argument('--workload', type=str, default='blender', choices=['blender', 'llff'],

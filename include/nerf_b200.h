@@ -97,6 +97,12 @@ int nb_raygen_pinhole(nb_handle_t h, int32_t H, int32_t W, double fx, double fy,
                       const float* pose, int64_t pose_ld, const int64_t* pix_idx, int64_t N,
                       float* rays_o, float* rays_d, unsigned flags, double ndc_focal, double ndc_near,
                       void* stream);
+/* rays.py:7-17 get_rays_np, the global-batch precompute (main.py:95-101), bit-exact: under NumPy >= 2 the float64 entries of K
+ * promote the whole computation to float64, so rays_d [H*W,3] is DOUBLE here: x=(c-cx)/fx, y=-((r-cy)/fy),
+ * d_k = ((x*R[k][0]) + (y*R[k][1])) + (-1*R[k][2]), each operation rounded in fp64 (no FMA).  rays_o is pose[:,3] broadcast
+ * (host side).  pose: 3x4 (or 3x3) row-major fp32 with pose_ld floats between rows. */
+int nb_raygen_pinhole_f64(nb_handle_t h, int32_t H, int32_t W, double fx, double fy, double cx, double cy, const float* pose,
+                          int64_t pose_ld, double* rays_d, void* stream);
 /* nerf_process.py:8-28 ndc_rays on arbitrary rays [N,3] (the global-batch path). In-place allowed. */
 int nb_ndc_rays(nb_handle_t h, int64_t N, int32_t H, int32_t W, double focal, double near,
                 const float* rays_o, const float* rays_d, float* o_out, float* d_out, void* stream);
@@ -115,7 +121,11 @@ int nb_select_pixels(nb_handle_t h, int64_t N, int32_t H, int32_t W, int32_t r0,
  * computed once by the caller from torch.linspace).  t_rand NULL => in-kernel Philox4x32-10
  * keyed by (seed, offset). */
 int nb_stratified(nb_handle_t h, int64_t N, int32_t S_c, const float* lower, const float* span,
-                  const float* t_rand, uint64_t seed, uint64_t offset, float* z_out, void* stream);
+                  const float* t_rand, uint64_t seed, uint64_t offset, const uint64_t* ctr, float* z_out, void* stream);
+/* Philox counters may live on the device: every sampling entry takes `ctr` (device pointer to one uint64, or NULL) whose value is
+ * ADDED to `offset` inside the kernel; nb_counter_add advances it in stream order.  A captured CUDA graph of a train step can
+ * then be replayed without any per-step host value. */
+int nb_counter_add(nb_handle_t h, uint64_t* ctr, uint64_t delta, void* stream);
 /* nerf_process.py:62-67 + 144-182: mids, pdf, cdf, inverse-CDF sampling, merge with z_c, sort.
  * u_mode 0: u is [S_f] shared by all rays (det=True: torch.linspace); 1: u is [N,S_f] (injected
  * torch.rand); 2: u NULL, Philox(seed, offset).  cdf_in (optional, [N,S_c-1]) overrides the
@@ -133,7 +143,7 @@ int nb_stratified(nb_handle_t h, int64_t N, int32_t S_c, const float* lower, con
 int nb_sample_pdf(nb_handle_t h, int64_t N, int32_t S_c, int32_t S_f, const float* z_c, const float* weights_c,
                   const float* u, int32_t u_mode, uint64_t seed, uint64_t offset, const float* cdf_in,
                   const float* bins_in, float* z_fine, float* z_samples, int64_t* inds, float* cdf_out, int64_t cdf_rows,
-                  void* stream);
+                  const uint64_t* ctr, void* stream);
 
 /* ---- K3: positional encoding (materialised form) ---------------------------------------- */
 /* model/PositionalEncoding.py:29-30: out[p] = [x, sin(2^k x), cos(2^k x)]_{k<L}; out is [P, 3+6L]. */
@@ -201,6 +211,14 @@ int nb_mse_grad(nb_handle_t h, int64_t N, const float* rgb, const float* target,
 int nb_adam_step(nb_handle_t h, int64_t n, float* p, const float* g, float* m, float* v, float lr, float beta1,
                  float beta2, float eps, int32_t step, void* stream);
 
+/* Data-parallel form: the gradient all-reduce folded into Adam's load.  srcs: HOST array of n_srcs (<= NB_MAX_RANKS)
+ * device pointers to the per-rank gradient buffers in RANK order (the caller's own buffer at its rank's position, the peers'
+ * copies -- delivered into this GPU's memory over NVLink by the copy engines during the backward -- elsewhere); the kernel
+ * sums them in that order (bit-identical on every rank), stores the sum in g, and applies nb_adam_step's update. */
+#define NB_MAX_RANKS 16
+int nb_adam_step_sum(nb_handle_t h, int64_t n, float* p, float* g, const float* const* srcs, int32_t n_srcs, float* m, float* v,
+                     float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+
 /* ---- fused drivers (nb_render_rays) ------------------------------------------ */
 /* Sampling configuration shared by the two drivers below.  lower/span are nb_stratified's [S_c] arrays.
  * u_mode as in nb_sample_pdf (0: u[S_f] shared = perturb==0, 1: u[N,S_f] injected, 2: Philox);
@@ -211,6 +229,7 @@ typedef struct nb_render_cfg {
   int32_t u_mode;
   uint64_t seed, offset_c, offset_f;
   int64_t cdf_rows;   /* nb_sample_pdf's cdf_rows (summation order of the fine pdf/cdf) */
+  const uint64_t* ctr; /* optional device-resident Philox counter added to offset_c / offset_f (nb_counter_add) */
 } nb_render_cfg;
 /* Bytes of caller workspace the drivers need for N rays (train != 0: including the activation stash). */
 int nb_render_workspace_bytes(nb_handle_t h, const nb_mlp_desc* d, int64_t N, const nb_render_cfg* cfg, int32_t train,

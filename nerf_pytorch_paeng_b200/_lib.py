@@ -27,7 +27,7 @@ class MlpDesc(C.Structure):
 
 class RenderCfg(C.Structure):
     _fields_ = [('S_c', C.c_int32), ('S_f', C.c_int32), ('precision', C.c_int32), ('u_mode', C.c_int32),
-                ('seed', C.c_uint64), ('offset_c', C.c_uint64), ('offset_f', C.c_uint64), ('cdf_rows', C.c_int64)]
+                ('seed', C.c_uint64), ('offset_c', C.c_uint64), ('offset_f', C.c_uint64), ('cdf_rows', C.c_int64), ('ctr', C.c_void_p)]
 
 
 _p = C.c_void_p
@@ -44,11 +44,13 @@ SIGNATURES = {
     'nb_device_info': (C.c_int, [_p, C.POINTER(_i32 * 4)]),
     'nb_launch_count': (_i64, [_p]),
     'nb_raygen_pinhole': (C.c_int, [_p, _i32, _i32, _f64, _f64, _f64, _f64, _p, _i64, _p, _i64, _p, _p, _u32, _f64, _f64, _p]),
+    'nb_raygen_pinhole_f64': (C.c_int, [_p, _i32, _i32, _f64, _f64, _f64, _f64, _p, _i64, _p, _p]),
     'nb_ndc_rays': (C.c_int, [_p, _i64, _i32, _i32, _f64, _f64, _p, _p, _p, _p, _p]),
     'nb_gather_rows': (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p]),
     'nb_select_pixels': (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _u64, _u64, _p, _p]),
-    'nb_stratified': (C.c_int, [_p, _i64, _i32, _p, _p, _p, _u64, _u64, _p, _p]),
-    'nb_sample_pdf': (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _i32, _u64, _u64, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    'nb_stratified': (C.c_int, [_p, _i64, _i32, _p, _p, _p, _u64, _u64, _p, _p, _p]),
+    'nb_counter_add': (C.c_int, [_p, _p, _u64, _p]),
+    'nb_sample_pdf': (C.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _i32, _u64, _u64, _p, _p, _p, _p, _p, _p, _i64, _p, _p]),
     'nb_posenc': (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     'nb_embed_points': (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _i64, _p]),
     'nb_mlp_act_bytes': (C.c_int, [_p, _desc, _i64, _i32, C.POINTER(_sz)]),
@@ -69,6 +71,7 @@ SIGNATURES = {
     'nb_frame_to8b': (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p]),
     'nb_mse_grad': (C.c_int, [_p, _i64, _p, _p, _f32, _f32, _p, _p, _p]),
     'nb_adam_step': (C.c_int, [_p, _i64, _p, _p, _p, _p, _f32, _f32, _f32, _f32, _i32, _p]),
+    'nb_adam_step_sum': (C.c_int, [_p, _i64, _p, _p, _p, _i32, _p, _p, _f32, _f32, _f32, _f32, _i32, _p]),
 }
 
 _lib = None

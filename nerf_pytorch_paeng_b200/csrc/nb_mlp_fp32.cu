@@ -106,18 +106,27 @@ struct Ctx {
 // forward: C = act(A.W^T (+C) (+b))
 int gemm_nt(Ctx& c, long long M, int N, int K, const float* A, long long lda, const float* W, long long ldw, float* C,
             long long ldc, const float* bias, unsigned flags) {
-  dim3 grid(nb_cdiv(N, BN), nb_cdiv(M, BM), 1);
-  sgemm_kernel<false, false><<<grid, 256, 0, c.st>>>((int)M, N, K, A, lda, W, ldw, C, ldc, bias, nullptr, 0, flags, K);
-  NB_LAUNCHED(c.h);
+  // point tiles ride on grid.y (<= 65535 blocks): larger calls are issued as row slabs
+  const long long slab = 65535LL * BM;
+  for (long long m0 = 0; m0 < M; m0 += slab) {
+    const long long rows = (M - m0 < slab) ? (M - m0) : slab;
+    dim3 grid(nb_cdiv(N, BN), nb_cdiv(rows, BM), 1);
+    sgemm_kernel<false, false><<<grid, 256, 0, c.st>>>((int)rows, N, K, A + m0 * lda, lda, W, ldw, C + m0 * ldc, ldc, bias, nullptr, 0, flags, K);
+    NB_LAUNCHED(c.h);
+  }
   return NB_OK;
 }
 // dgrad: C = (A.W) [masked by mask>0]
 int gemm_nn(Ctx& c, long long M, int N, int K, const float* A, long long lda, const float* W, long long ldw, float* C,
             long long ldc, const float* mask, long long ld_mask, unsigned flags) {
-  dim3 grid(nb_cdiv(N, BN), nb_cdiv(M, BM), 1);
-  sgemm_kernel<false, true><<<grid, 256, 0, c.st>>>((int)M, N, K, A, lda, W, ldw, C, ldc, nullptr, mask, ld_mask,
-                                                     flags | (mask ? F_MASK : 0), K);
-  NB_LAUNCHED(c.h);
+  const long long slab = 65535LL * BM;
+  for (long long m0 = 0; m0 < M; m0 += slab) {
+    const long long rows = (M - m0 < slab) ? (M - m0) : slab;
+    dim3 grid(nb_cdiv(N, BN), nb_cdiv(rows, BM), 1);
+    sgemm_kernel<false, true><<<grid, 256, 0, c.st>>>((int)rows, N, K, A + m0 * lda, lda, W, ldw, C + m0 * ldc, ldc, nullptr,
+                                                       mask ? mask + m0 * ld_mask : nullptr, ld_mask, flags | (mask ? F_MASK : 0), K);
+    NB_LAUNCHED(c.h);
+  }
   return NB_OK;
 }
 // wgrad: C[M=out, N=in] += dY[P,out]^T . X[P,in], split-K with atomics (C must be initialised)

@@ -46,6 +46,29 @@ adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g, flo
   }
 }
 
+// Data-parallel variant: the gradient all-reduce is folded into Adam's load.  Every rank holds the gradient
+// buffers of all ranks (its own, plus the peers' copies that arrived over NVLink through the copy engines while the backward was
+// still running); this kernel sums them IN RANK ORDER (so every rank computes bit-identical sums and the replicas never diverge),
+// writes the sum back to g (p.grad then holds the all-reduced gradient) and applies the update.
+struct GradSrcs { const float* src[NB_MAX_RANKS]; int n; };
+
+__global__ void __launch_bounds__(256)
+adam_sum_kernel(long long n, float* __restrict__ p, float* __restrict__ g, GradSrcs s, float* __restrict__ m, float* __restrict__ v,
+                float beta1, float beta2, float eps, float step_size, float inv_bc2_sqrt) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gi = s.src[0][i];
+    for (int r = 1; r < s.n; ++r) gi += s.src[r][i];
+    g[i] = gi;
+    const float mi = m[i] + (gi - m[i]) * (1.0f - beta1);
+    const float vi = v[i] * beta2 + (gi * gi) * (1.0f - beta2);
+    const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
 // frame output (test.py:50-61, utils.py:11): rgb8 = to8b(rgb), disp8 = to8b(disp / nanmax(disp))
 __global__ void __launch_bounds__(256)
 nanmax_kernel(long long n, const float* __restrict__ x, float* __restrict__ out) {
@@ -124,6 +147,27 @@ extern "C" int nb_adam_step(nb_handle_t h, int64_t n, float* p, const float* g, 
   const long long cap = (long long)h->sm_count * 8;
   if (blocks > cap) blocks = cap;
   adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((long long)n, p, g, m, v, beta1, beta2, eps, step_size, inv_bc2_sqrt);
+  NB_LAUNCHED(h);
+  return NB_OK;
+}
+
+extern "C" int nb_adam_step_sum(nb_handle_t h, int64_t n, float* p, float* g, const float* const* srcs, int32_t n_srcs, float* m,
+                                float* v, float lr, float beta1, float beta2, float eps, int32_t step, void* stream) {
+  NB_ENTER(h);
+  NB_REQUIRE(h, n >= 0 && p && g && srcs && m && v && step >= 1 && n_srcs >= 1 && n_srcs <= NB_MAX_RANKS, "nb_adam_step_sum: bad arguments");
+  if (n == 0) return NB_OK;
+  GradSrcs s;
+  s.n = n_srcs;
+  for (int i = 0; i < NB_MAX_RANKS; ++i) s.src[i] = i < n_srcs ? srcs[i] : nullptr;
+  for (int i = 0; i < n_srcs; ++i) NB_REQUIRE(h, srcs[i], "nb_adam_step_sum: NULL gradient source");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)h->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  adam_sum_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((long long)n, p, g, s, m, v, beta1, beta2, eps, step_size, inv_bc2_sqrt);
   NB_LAUNCHED(h);
   return NB_OK;
 }

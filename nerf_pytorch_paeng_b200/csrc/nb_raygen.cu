@@ -164,6 +164,34 @@ extern "C" int nb_raygen_pinhole(nb_handle_t h, int32_t H, int32_t W, double fx,
   return NB_OK;
 }
 
+// rays.py:7-17 get_rays_np as NumPy >= 2 evaluates it: float32 pixel grids and pose, float64 K scalars (NEP 50) => every
+// operation in float64, individually rounded: d_k = ((x*R[k][0]) + (y*R[k][1])) + (z*R[k][2]) with z = -1.
+__global__ void __launch_bounds__(256)
+raygen_f64_kernel(int W, double fx, double fy, double cx, double cy, const float* __restrict__ pose, long long pose_ld, long long N,
+                  double* __restrict__ rays_d) {
+  __shared__ double sr[9];
+  if (threadIdx.x < 9) sr[threadIdx.x] = (double)pose[(threadIdx.x / 3) * pose_ld + (threadIdx.x % 3)];
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one output component per thread: coalesced 8-byte stores
+  if (i >= 3 * N) return;
+  const long long p = i / 3;
+  const int k = (int)(i - 3 * p);
+  const int r = (int)(p / W), c = (int)(p - (long long)r * W);
+  const double x = __ddiv_rn(__dsub_rn((double)c, cx), fx);
+  const double y = -__ddiv_rn(__dsub_rn((double)r, cy), fy);
+  rays_d[i] = __dadd_rn(__dadd_rn(__dmul_rn(x, sr[k * 3 + 0]), __dmul_rn(y, sr[k * 3 + 1])), __dmul_rn(-1.0, sr[k * 3 + 2]));
+}
+
+extern "C" int nb_raygen_pinhole_f64(nb_handle_t h, int32_t H, int32_t W, double fx, double fy, double cx, double cy, const float* pose,
+                                     int64_t pose_ld, double* rays_d, void* stream) {
+  NB_ENTER(h);
+  NB_REQUIRE(h, H > 0 && W > 0 && pose && rays_d && pose_ld >= 3 && fx != 0. && fy != 0., "nb_raygen_pinhole_f64: bad arguments");
+  const long long N = (long long)H * W;
+  raygen_f64_kernel<<<nb_cdiv(3 * N, 256), 256, 0, (cudaStream_t)stream>>>(W, fx, fy, cx, cy, pose, (long long)pose_ld, N, rays_d);
+  NB_LAUNCHED(h);
+  return NB_OK;
+}
+
 extern "C" int nb_ndc_rays(nb_handle_t h, int64_t N, int32_t H, int32_t W, double focal, double near,
                            const float* rays_o, const float* rays_d, float* o_out, float* d_out, void* stream) {
   NB_ENTER(h);

@@ -65,9 +65,9 @@ int run_net(nb_handle_t h, const nb_mlp_desc* d, const nb_render_cfg* c, const P
   const int32_t S = fine ? c->S_c + c->S_f : c->S_c;
   float* z = fine ? p.z_f : p.z_c;
   float* w = fine ? p.w_f : p.w_c;
-  if (!fine) rc = nb_stratified(h, N, c->S_c, lower, span, t_rand, c->seed, c->offset_c, z, st);
+  if (!fine) rc = nb_stratified(h, N, c->S_c, lower, span, t_rand, c->seed, c->offset_c, c->ctr, z, st);
   else rc = nb_sample_pdf(h, N, c->S_c, c->S_f, p.z_c, p.w_c, u, c->u_mode, c->seed, c->offset_f, nullptr, nullptr, z, nullptr,
-                          nullptr, nullptr, c->cdf_rows, st);
+                          nullptr, nullptr, c->cdf_rows, c->ctr, st);
   if (rc) return rc;
   if ((rc = nb_mlp_forward_rays(h, d, params, packed, N, S, rays, z, p.raw, train ? p.act : nullptr, c->precision, p.mlp_ws,
                                 p.mlp_ws_bytes, st))) return rc;

@@ -17,8 +17,9 @@ namespace {
 __global__ void __launch_bounds__(256)
 stratified_kernel(long long total4, int S, const float* __restrict__ lower, const float* __restrict__ span,
                   const float4* __restrict__ t_rand, uint2 key, unsigned long long offset,
-                  float4* __restrict__ z_out) {
+                  const unsigned long long* __restrict__ ctr, float4* __restrict__ z_out) {
   extern __shared__ float s_ls[];  // lower[S], span[S]
+  if (ctr) offset += *ctr;         // device-resident Philox counter (CUDA-graph replays advance it without host work)
   for (int i = threadIdx.x; i < S; i += blockDim.x) { s_ls[i] = lower[i]; s_ls[S + i] = span[i]; }
   __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -56,8 +57,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 sample_pdf_kernel(long long N, int S_c, int S_f, int P2, const float* __restrict__ z_c, const float* __restrict__ w_c,
                   const float* __restrict__ u_in, int u_mode, uint2 key, unsigned long long offset,
                   const float* __restrict__ cdf_in, const float* __restrict__ bins_in, float* __restrict__ z_fine,
-                  float* __restrict__ z_samples, long long* __restrict__ inds_out, float* __restrict__ cdf_out, int scan_ntx, int sum_bw) {
+                  float* __restrict__ z_samples, long long* __restrict__ inds_out, float* __restrict__ cdf_out, int scan_ntx, int sum_bw,
+                  const unsigned long long* __restrict__ ctr) {
   extern __shared__ float smem[];
+  if (ctr) offset += *ctr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per_warp = 3 * S_c + P2;
   float* sz = smem + warp * per_warp;
@@ -293,8 +296,18 @@ sample_pdf_kernel(long long N, int S_c, int S_f, int P2, const float* __restrict
 
 }  // namespace
 
+__global__ void counter_add_kernel(unsigned long long* ctr, unsigned long long delta) { *ctr += delta; }
+
+extern "C" int nb_counter_add(nb_handle_t h, uint64_t* ctr, uint64_t delta, void* stream) {
+  NB_ENTER(h);
+  NB_REQUIRE(h, ctr, "nb_counter_add: NULL counter");
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)ctr, (unsigned long long)delta);
+  NB_LAUNCHED(h);
+  return NB_OK;
+}
+
 extern "C" int nb_stratified(nb_handle_t h, int64_t N, int32_t S_c, const float* lower, const float* span,
-                             const float* t_rand, uint64_t seed, uint64_t offset, float* z_out, void* stream) {
+                             const float* t_rand, uint64_t seed, uint64_t offset, const uint64_t* ctr, float* z_out, void* stream) {
   NB_ENTER(h);
   NB_REQUIRE(h, N >= 0 && S_c > 0 && S_c % 4 == 0 && S_c <= 2048 && lower && span && z_out,
              "nb_stratified: need S_c %% 4 == 0, S_c <= 2048 and non-null buffers");
@@ -305,7 +318,7 @@ extern "C" int nb_stratified(nb_handle_t h, int64_t N, int32_t S_c, const float*
   if (blocks > cap) blocks = cap;
   uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   stratified_kernel<<<blocks, 256, 2 * S_c * sizeof(float), (cudaStream_t)stream>>>(
-      total4, S_c, lower, span, (const float4*)t_rand, key, (unsigned long long)offset, (float4*)z_out);
+      total4, S_c, lower, span, (const float4*)t_rand, key, (unsigned long long)offset, (const unsigned long long*)ctr, (float4*)z_out);
   NB_LAUNCHED(h);
   return NB_OK;
 }
@@ -325,7 +338,7 @@ static int aten_scan_threads_x(uint64_t num_rows, uint32_t row_size) {
 extern "C" int nb_sample_pdf(nb_handle_t h, int64_t N, int32_t S_c, int32_t S_f, const float* z_c,
                              const float* weights_c, const float* u, int32_t u_mode, uint64_t seed, uint64_t offset,
                              const float* cdf_in, const float* bins_in, float* z_fine, float* z_samples, int64_t* inds,
-                             float* cdf_out, int64_t cdf_rows, void* stream) {
+                             float* cdf_out, int64_t cdf_rows, const uint64_t* ctr, void* stream) {
   NB_ENTER(h);
   NB_REQUIRE(h, N >= 0 && S_c >= 3 && S_f > 0 && S_c + S_f <= 4096, "nb_sample_pdf: bad sizes");
   NB_REQUIRE(h, z_c || (bins_in && !z_fine), "nb_sample_pdf: z_c may be NULL only with bins_in and without z_fine");
@@ -347,7 +360,7 @@ extern "C" int nb_sample_pdf(nb_handle_t h, int64_t N, int32_t S_c, int32_t S_f,
   const size_t smem = (size_t)kWarpsPerBlock * (3 * S_c + P2) * sizeof(float);
   NB_REQUIRE(h, smem <= 200 * 1024, "nb_sample_pdf: S_c/S_f too large for shared memory");
   typedef void (*pdf_kernel_t)(long long, int, int, int, const float*, const float*, const float*, int, uint2, unsigned long long,
-                               const float*, const float*, float*, float*, long long*, float*, int, int);
+                               const float*, const float*, float*, float*, long long*, float*, int, int, const unsigned long long*);
   pdf_kernel_t kern = sample_pdf_kernel<0>;
   if (z_fine && S_f <= 2 * S_c) {
     if (S_f == 128) kern = sample_pdf_kernel<4>;
@@ -362,7 +375,7 @@ extern "C" int nb_sample_pdf(nb_handle_t h, int64_t N, int32_t S_c, int32_t S_f,
   uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   kern<<<(int)blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
       (long long)N, S_c, S_f, P2, z_c, weights_c, u, u_mode, key, (unsigned long long)offset, cdf_in, bins_in, z_fine,
-      z_samples, (long long*)inds, cdf_out, scan_ntx, sum_bw);
+      z_samples, (long long*)inds, cdf_out, scan_ntx, sum_bw, (const unsigned long long*)ctr);
   NB_LAUNCHED(h);
   return NB_OK;
 }

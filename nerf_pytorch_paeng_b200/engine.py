@@ -83,6 +83,14 @@ class Engine:
                    _ptr(o), _ptr(d), _lib.NB_RAYGEN_NDC if ndc else 0, float(ndc_focal), float(ndc_near), self.stream)
         return o, d
 
+    def raygen_f64(self, H, W, K, pose):
+        """rays.py:7-17 as NumPy >= 2 computes it (float64 throughout): rays_d [H*W,3] float64."""
+        fx, fy, cx, cy = float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2])
+        pose = pose if (pose.dtype == torch.float32 and pose.stride(-1) == 1) else pose.float().contiguous()
+        d = self.empty(H * W, 3, dtype=torch.float64)
+        self._call('nb_raygen_pinhole_f64', H, W, fx, fy, cx, cy, _ptr(pose), pose.stride(0), _ptr(d), self.stream)
+        return d
+
     def ndc_rays(self, H, W, focal, near, rays_o, rays_d):
         o = _chk32(rays_o.reshape(-1, 3), 'rays_o')
         d = _chk32(rays_d.reshape(-1, 3), 'rays_d')
@@ -113,7 +121,7 @@ class Engine:
             t_rand = _chk32(t_rand, 't_rand')
             assert t_rand.shape == (n_rays, s_c)
         z = self.empty(n_rays, s_c)
-        self._call('nb_stratified', n_rays, s_c, _ptr(lower), _ptr(span), _ptr(t_rand), seed, offset, _ptr(z), self.stream)
+        self._call('nb_stratified', n_rays, s_c, _ptr(lower), _ptr(span), _ptr(t_rand), seed, offset, None, _ptr(z), self.stream)
         return z
 
     def sample_pdf(self, z_c, weights_c, n_fine, u=None, seed=0, offset=0, cdf_in=None, bins_in=None, want_fine=True,
@@ -146,7 +154,7 @@ class Engine:
         inds = self.empty(n, n_fine, dtype=torch.int64) if want_inds else None
         cdf = self.empty(n, s_c - 1) if want_cdf else None
         self._call('nb_sample_pdf', n, s_c, n_fine, _ptr(z_c), _ptr(weights_c), _ptr(u), mode, seed, offset, _ptr(cdf_in),
-                   _ptr(bins_in), _ptr(z_f), _ptr(zs), _ptr(inds), _ptr(cdf), int(cdf_rows), self.stream)
+                   _ptr(bins_in), _ptr(z_f), _ptr(zs), _ptr(inds), _ptr(cdf), int(cdf_rows), None, self.stream)
         return z_f, zs, inds, cdf
 
     # ------------------------------------------------------------------ K3
@@ -262,12 +270,13 @@ class Engine:
     def _u_mode(u):
         return 2 if u is None else (0 if u.dim() == 1 else 1)
 
-    def render_rays(self, desc, nets, rays, lower, span, n_fine, precision, t_rand=None, u=None, seed=0, offset_c=0, offset_f=0, cdf_rows=0):
+    def render_rays(self, desc, nets, rays, lower, span, n_fine, precision, t_rand=None, u=None, seed=0, offset_c=0, offset_f=0, cdf_rows=0, ctr=None):
         """nerf_process.py:185-216 as one nb_render_rays call.  nets = ((flat_c, packed_c), (flat_f, packed_f)).
         Returns (rgb_c, disp_c, rgb_f, disp_f); the fine pair is None when n_fine == 0."""
         rays = _chk32(rays, 'rays')
         n = rays.shape[0]
-        cfg = RenderCfg(lower.numel(), max(int(n_fine), 0), precision, self._u_mode(u), seed, offset_c, offset_f, int(cdf_rows))
+        cfg = RenderCfg(lower.numel(), max(int(n_fine), 0), precision, self._u_mode(u), seed, offset_c, offset_f, int(cdf_rows),
+                        None if ctr is None else ctr.data_ptr())
         ws = self._fused_ws(desc, n, cfg, False)
         (pc, kc), (pf, kf) = nets
         rgb_c, disp_c = self.empty(n, 3), self.empty(n)
@@ -278,13 +287,14 @@ class Engine:
         return rgb_c, disp_c, rgb_f, disp_f
 
     def train_rays(self, desc, nets, grads, rays, target, n_global, lower, span, n_fine, precision, loss_buf, out, which=3,
-                   t_rand=None, u=None, seed=0, offset_c=0, offset_f=0, accumulate=False, target_ready=None, cdf_rows=0):
+                   t_rand=None, u=None, seed=0, offset_c=0, offset_f=0, accumulate=False, target_ready=None, cdf_rows=0, ctr=None):
         """train.py:53-69 minus the optimizer as nb_train_rays.  `out` is a dict that receives / supplies the
         rgb_c, disp_c, rgb_f, disp_f tensors (so a coarse call and a fine call can share it); which = nets bit mask."""
         rays = _chk32(rays, 'rays')
         target = _chk32(target, 'target')
         n = rays.shape[0]
-        cfg = RenderCfg(lower.numel(), max(int(n_fine), 0), precision, self._u_mode(u), seed, offset_c, offset_f, int(cdf_rows))
+        cfg = RenderCfg(lower.numel(), max(int(n_fine), 0), precision, self._u_mode(u), seed, offset_c, offset_f, int(cdf_rows),
+                        None if ctr is None else ctr.data_ptr())
         ws = self._fused_ws(desc, n, cfg, True)
         (pc, kc), (pf, kf) = nets
         for tag, bit in (('c', 1), ('f', 2)):
@@ -318,6 +328,16 @@ class Engine:
         self._call('nb_mse_grad', rgb.shape[0], _ptr(rgb), _ptr(target), float(scale), float(loss_scale), _ptr(d),
                    _ptr(loss_out), self.stream)
         return d
+
+    def adam_step_sum(self, p, g, srcs, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+        """Adam on g := sum(srcs) (rank-ordered list of equally shaped device tensors / pointers)."""
+        arr = (C.c_void_p * len(srcs))(*[t if isinstance(t, int) else t.data_ptr() for t in srcs])
+        self._call('nb_adam_step_sum', p.numel(), _ptr(p), _ptr(g), arr, len(srcs), _ptr(m), _ptr(v), float(lr), beta1, beta2, eps,
+                   int(step), self.stream)
+
+    def counter_add(self, ctr, delta):
+        """ctr (device int64/uint64 scalar tensor) += delta, in stream order (graph-capturable)."""
+        self._call('nb_counter_add', _ptr(ctr), int(delta), self.stream)
 
     def adam_step(self, p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
         self._call('nb_adam_step', p.numel(), _ptr(p), _ptr(g), _ptr(m), _ptr(v), float(lr), beta1, beta2, eps, int(step),

@@ -2,8 +2,8 @@
 
 Same constructor, sub-module names and state_dict keys as NeRF.py:10-30,55-65
 (``model_{coarse,fine}.linear_x.{0..D-1}``, ``linear_d``, ``linear_feat``, ``linear_density``,
-``linear_color``), same Xavier-uniform init consumed in the same RNG order, so checkpoints and
-optimisers are interchangeable.  ``forward`` runs the CUDA MLP (K4) instead of nn.Linear/cuBLAS:
+``linear_color``), same Xavier-uniform init consumed in the same RNG order, so checkpoints are
+interchangeable (optimizer state: trainer.FlatAdam speaks torch.optim.Adam's state_dict format).  ``forward`` runs the CUDA MLP (K4) instead of nn.Linear/cuBLAS:
 
 * every parameter of one NeRFModule is a view into ONE flat fp32 buffer laid out in
   ``parameters()`` order (the layout of nb_mlp_desc in include/nerf_b200.h); gradients likewise.
@@ -88,9 +88,9 @@ class NeRFModule(nn.Module):
                 return
         params = self._plist = tuple(self.parameters())
         self._flat_dirty = False
+        # host storage is allowed (checkpoint / optimizer-state handling); every COMPUTE entry point goes through get_engine(),
+        # which raises on a non-CUDA device: there is no CPU fallback
         dev = params[0].device
-        if dev.type != 'cuda':
-            raise NBError('NeRF parameters must live on a CUDA device: there is no CPU fallback')
         total = sum(p.numel() for p in params)
         ok = self.flat is not None and self.flat.device == dev and self.flat.numel() == total
         if ok:
@@ -184,6 +184,8 @@ class NeRF(nn.Module):
     def set_precision(self, precision):
         if precision in ('fp32', 'bf16'):
             precision = {'fp32': NB_FP32, 'bf16': NB_BF16}[precision]
+        if precision not in (NB_FP32, NB_BF16):
+            raise NBError(f'unknown precision {precision!r} (use "bf16" or "fp32")')
         self.model_coarse.precision = precision
         self.model_fine.precision = precision
         return self

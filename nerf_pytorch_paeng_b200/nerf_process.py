@@ -9,7 +9,7 @@ from ``opts.rng`` when present -- a dict with injected tensors {'t_rand': [N,S_c
 """
 import torch
 
-from .engine import get_engine
+from .engine import NB_BF16, get_engine
 from .model.NeRF import NeRF
 
 _zlin_cache = {}
@@ -45,6 +45,33 @@ def _next_offset(n):
     return off
 
 
+def rng_state():
+    """Philox counter of this process' sampling stream (saved in checkpoints by train.train so that a resumed run does not
+    replay the draws of the first steps)."""
+    return int(_counter[0])
+
+
+def set_rng_state(v):
+    _counter[0] = int(v)
+
+
+def _seed(opts):
+    """Philox key: opts.seed decorrelated per data-parallel rank (every rank of train() gets the same opts.seed, and ray i of
+    every rank would otherwise see identical stratified / pdf draws)."""
+    seed = int(getattr(opts, 'seed', 0))
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        seed += 0x9E3779B1 * torch.distributed.get_rank()
+    return seed & 0xFFFFFFFFFFFFFFFF
+
+
+def apply_precision(model, opts):
+    """opts.precision ('bf16' | 'fp32', config.py --precision, default bf16) selects the MLP path of the drop-in entry points;
+    hand-built opts without the attribute leave the module's own setting alone."""
+    prec = getattr(opts, 'precision', None)
+    if prec is not None and isinstance(model, NeRF):
+        model.set_precision(prec)
+
+
 def _cdf_rows(opts, n):
     """Summation order of the fine pdf/cdf (nb_sample_pdf's cdf_rows).  Default: torch's CUDA order for the call the REFERENCE
     would make -- n rows, or opts.chunk_rays when this engine is handed a larger chunk than the reference's batchify loop uses
@@ -71,7 +98,7 @@ def _coarse_z(rays, opts):
     lower, span = _coarse_bins(opts, rays.device)
     n = rays.shape[0]
     t_rand = _injected(opts, 't_rand')
-    return eng.stratified(n, lower, span, t_rand=t_rand, seed=int(getattr(opts, 'seed', 0)),
+    return eng.stratified(n, lower, span, t_rand=t_rand, seed=_seed(opts),
                           offset=_next_offset(n * opts.N_samples_c // 4 + 1))
 
 
@@ -85,7 +112,7 @@ def _fine_z(rays, opts, z_vals, weights):
         u = _u_det_cache[key]
     else:
         u = _injected(opts, 'u')
-    z_fine, _, _, _ = eng.sample_pdf(z_vals, weights.detach(), opts.N_samples_f, u=u, seed=int(getattr(opts, 'seed', 0)),
+    z_fine, _, _, _ = eng.sample_pdf(z_vals, weights.detach(), opts.N_samples_f, u=u, seed=_seed(opts),
                                      offset=_next_offset(n * opts.N_samples_f // 4 + 1), cdf_rows=_cdf_rows(opts, n))
     return z_fine
 
@@ -107,7 +134,7 @@ def _fused_sampling_args(n, opts, device):
         else:
             u = _injected(opts, 'u')
         off_f = _next_offset(n * n_fine // 4 + 1)
-    return dict(lower=lower, span=span, n_fine=n_fine, t_rand=_injected(opts, 't_rand'), u=u, seed=int(getattr(opts, 'seed', 0)),
+    return dict(lower=lower, span=span, n_fine=n_fine, t_rand=_injected(opts, 't_rand'), u=u, seed=_seed(opts),
                 offset_c=off_c, offset_f=off_f, cdf_rows=_cdf_rows(opts, n))
 
 
@@ -167,7 +194,7 @@ def sample_pdf(bins, weights, N_samples, det=False, opts=None):
     else:
         u = _injected(opts, 'u')
     _, samples, _, _ = eng.sample_pdf(None, w_pad, N_samples, u=u, bins_in=bins, want_samples=True,
-                                      seed=int(getattr(opts, 'seed', 0)), offset=_next_offset(n * N_samples // 4 + 1),
+                                      seed=_seed(opts), offset=_next_offset(n * N_samples // 4 + 1),
                                       cdf_rows=-1 if getattr(opts, 'cdf_order', 'cuda') == 'fp64' else n)
     return samples
 
@@ -180,6 +207,7 @@ def render_rays(rays, model, posenc, opts):
     """nerf_process.py:185-216.  rays [N,6] -> dict(rgb_c, disp_c[, rgb_f, disp_f])."""
     if not isinstance(model, NeRF):
         raise TypeError('render_rays needs the nerf_pytorch_paeng_b200.model.NeRF module (CUDA path only)')
+    apply_precision(model, opts)
     rays = rays.contiguous()
     rays_d = rays[:, 3:].contiguous()
     # 1-a/2-a) coarse depths, fused points+PE+MLP (chunk_pts is a memory knob of the reference; the

@@ -14,13 +14,15 @@ def _as_cuda_pose(pose, device=None):
 
 
 def get_rays_np(H, W, K, c2w):
-    """rays.py:7-17.  Same geometry as make_o_d, returned as host NumPy arrays [H,W,3] for the
-    global-batch precompute (main.py:95-101).  Computed by the CUDA ray-gen kernel in fp32: the
-    reference's NumPy>=2 result is float64 and differs from the fp32 path by <=1 ulp (SURVEY A2);
-    main.py:101 casts to float32 anyway."""
+    """rays.py:7-17.  Host NumPy arrays for the global-batch precompute (main.py:95-101), bit-exact with the reference under
+    NumPy >= 2: K's float64 entries promote the computation to float64, so rays_d is float64 [H,W,3] (computed by
+    the fp64 ray-gen kernel with the same individually rounded operations) and rays_o is the float32 c2w[:3,-1] broadcast to
+    that shape (a read-only view, like np.broadcast_to in the reference).  main.py:101 casts the stack to float32."""
+    c2w_np = np.asarray(c2w.detach().cpu() if isinstance(c2w, torch.Tensor) else c2w)
     pose = _as_cuda_pose(c2w)
-    o, d = get_engine(pose.device).raygen(H, W, K, pose)
-    return o.reshape(H, W, 3).cpu().numpy(), d.reshape(H, W, 3).cpu().numpy()
+    d = get_engine(pose.device).raygen_f64(H, W, _host_K(K), pose)
+    rays_d = d.reshape(H, W, 3).cpu().numpy()
+    return np.broadcast_to(c2w_np[:3, -1], rays_d.shape), rays_d
 
 
 def make_o_d(img_w, img_h, img_k, pose):

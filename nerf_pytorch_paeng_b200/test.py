@@ -10,14 +10,20 @@ import torch
 
 from . import trainer
 from .engine import get_engine
+from .nerf_process import apply_precision
 from .config import LOG_DIR
 from .utils import img2mse, mse2psnr, to8b
 
 
 def _load_checkpoint(model, opts, idx):
+    """test.py:20-21 / 128-130: the reference torch.load()s unconditionally, so a wrong idx / exp_name raises; so does this.
+    opts.allow_missing_checkpoint=True evaluates the weights already in memory instead (benchmarks, tests)."""
     path = os.path.join(LOG_DIR, opts.exp_name, opts.exp_name + '_{}.pth.tar'.format(idx))
-    if os.path.exists(path):                                   # test.py:20-21 / 128-130
-        model.load_state_dict(torch.load(path, map_location='cpu')['model_state_dict'])
+    if not os.path.exists(path):
+        if getattr(opts, 'allow_missing_checkpoint', False):
+            return
+        raise FileNotFoundError(f'checkpoint {path} not found (set opts.allow_missing_checkpoint=True to evaluate the weights in memory)')
+    model.load_state_dict(torch.load(path, map_location='cpu')['model_state_dict'])
 
 
 def _frames(model, poses, K, hw, opts, dist_ctx):
@@ -32,6 +38,7 @@ def _frames(model, poses, K, hw, opts, dist_ctx):
 def test(idx, i_test, posenc, model, test_imgs, gt_intrinsic, gt_extrinsic, hw, opts, dist_ctx=None, save=True):
     model.eval()
     _load_checkpoint(model, opts, idx)
+    apply_precision(model, opts)
     out_dir = os.path.join(LOG_DIR, opts.exp_name, opts.exp_name + '_{}'.format(idx), 'test_result')
     psnrs, frames = [], []
     for i, (rgb, disp) in enumerate(_frames(model, gt_extrinsic, gt_intrinsic, hw, opts, dist_ctx)):
@@ -51,6 +58,7 @@ def test(idx, i_test, posenc, model, test_imgs, gt_intrinsic, gt_extrinsic, hw, 
 def render(idx, posenc, model, gt_intrinsic, render_pose, hw, opts, dist_ctx=None, save=True):
     model.eval()
     _load_checkpoint(model, opts, idx)
+    apply_precision(model, opts)
     out_dir = os.path.join(LOG_DIR, opts.exp_name, opts.exp_name + '_{}'.format(idx), 'render_result')
     rgbs, disps = [], []
     for i, (rgb, disp) in enumerate(_frames(model, render_pose, gt_intrinsic, hw, opts, dist_ctx)):

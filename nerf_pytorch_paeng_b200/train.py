@@ -15,7 +15,7 @@ import torch
 
 from . import trainer
 from .config import LOG_DIR
-from .nerf_process import batchify_rays_and_render_by_chunk, ndc_rays
+from .nerf_process import _seed, apply_precision, batchify_rays_and_render_by_chunk, ndc_rays
 from .rays import make_o_d_selected
 from .utils import mse2psnr
 
@@ -34,8 +34,44 @@ def _device_copy(arr, device, key):
     """K / poses: the reference re-uploads them every step (train.py:18-21); here once per array."""
     k = (key, id(arr), str(device))
     if k not in _cache:
-        _cache[k] = torch.from_numpy(np.ascontiguousarray(arr)).to(device)
-    return _cache[k]
+        t = arr if isinstance(arr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(arr))
+        _cache[k] = (arr, t.to(device))            # keeps `arr` alive so that its id cannot be recycled
+    return _cache[k][1]
+
+
+_images = {}
+
+
+def _resident_image(images, i_img, device):
+    """Device copy [H*W,3] fp32 of images[i_img], uploaded once.  Keyed by the container's identity (a reference to it is kept
+    so the id cannot be recycled) and the image index."""
+    key = (id(images), str(device))
+    ent = _images.get(key)
+    if ent is None or ent[0] is not images:
+        if len(_images) > 8:
+            _images.clear()
+        ent = _images[key] = (images, {})
+    dev_imgs = ent[1]
+    t = dev_imgs.get(int(i_img))
+    if t is None:
+        img = images[i_img]
+        img = img if isinstance(img, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(img))
+        t = dev_imgs[int(i_img)] = img.to(device=device, dtype=torch.float32).reshape(-1, 3).contiguous()
+    return t
+
+
+def load_checkpoint(path, model, optimizer=None, map_location='cpu'):
+    """main.py:111-117 (resume): model + optimizer state of a checkpoint written by train() below OR by the reference
+    (train.py:105-114; its torch.optim.Adam state loads into trainer.FlatAdam); restores the sampling stream position when the
+    checkpoint carries it.  Returns the checkpoint's idx."""
+    from . import nerf_process
+    ck = torch.load(path, map_location=map_location)
+    model.load_state_dict(ck['model_state_dict'])
+    if optimizer is not None and 'optimizer_state_dict' in ck:
+        optimizer.load_state_dict(ck['optimizer_state_dict'])
+    if 'nb_rng_counter' in ck:
+        nerf_process.set_rng_state(ck['nb_rng_counter'])
+    return ck.get('idx', 0)
 
 
 def select_pixels(i, img_h, img_w, opts):
@@ -56,6 +92,7 @@ def train(idx, i_train, images, gt_cam_param, hw, model, criterion, posenc, opti
           dist_ctx=None):
     if not model.training:                      # train.py:14 (a full module-tree walk; skipped when already in training mode)
         model.train()
+    apply_precision(model, opts)
     device = torch.device(f'cuda:{opts.gpu_ids[opts.rank]}')
     img_h, img_w = hw
     gt_intrinsic, gt_extrinsic = gt_cam_param
@@ -69,7 +106,11 @@ def train(idx, i_train, images, gt_cam_param, hw, model, criterion, posenc, opti
             rays_o, rays_d = ndc_rays(img_h, img_w, float(gt_intrinsic[0][0]), 1., rays_o, rays_d)
     else:                                                                         # train.py:35-45
         i_img = np.random.choice(i_train)
-        pose = _device_copy(gt_extrinsic, device, 'poses')[i_img, :3, :4]
+        if getattr(opts, 'cache_poses', True):
+            pose = _device_copy(gt_extrinsic, device, 'poses')[i_img, :3, :4]
+        else:       # per-step upload of the selected camera (the reference uploads ALL poses every step, train.py:20-21)
+            ext = gt_extrinsic if isinstance(gt_extrinsic, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(gt_extrinsic))
+            pose = ext[i_img, :3, :4].to(device=device, dtype=torch.float32, non_blocking=True)
         if getattr(opts, 'device_select', False):
             # selection on the device (keyed bijection, distinct pixels, no host permutation)
             region = None
@@ -77,28 +118,35 @@ def train(idx, i_train, images, gt_cam_param, hw, model, criterion, posenc, opti
                 dH, dW = int(img_h // 2 * opts.precrop_frac), int(img_w // 2 * opts.precrop_frac)
                 region = (img_h // 2 - dH, img_w // 2 - dW, 2 * dH, 2 * dW)
             from .engine import get_engine as _ge
-            pix = _ge(device).select_pixels(opts.N_rays, img_h, img_w, region, seed=int(getattr(opts, 'seed', 0)) + 7919 * i_img,
+            pix = _ge(device).select_pixels(opts.N_rays, img_h, img_w, region, seed=_seed(opts) + 7919 * i_img,
                                             offset=idx * opts.N_rays)
         else:
             pix = torch.from_numpy(select_pixels(idx, img_h, img_w, opts)).to(device, non_blocking=True)
-        img = images[i_img]
-        img = img if isinstance(img, torch.Tensor) else torch.from_numpy(img)
-        # H2D of the target image (train.py:37-38) and the gather of the selected pixels (rays.py:62) on a side stream:
-        # the target is only needed at the first loss, so both overlap ray generation and the coarse forward
         from .engine import get_engine
-        main = torch.cuda.current_stream(device)
-        side = _side_stream(device)
-        pix_ready = torch.cuda.Event()
-        pix_ready.record(main)
-        with torch.cuda.stream(side):
-            img_dev = img.to(device=device, dtype=torch.float32, non_blocking=True)
-            side.wait_event(pix_ready)
-            tgt = get_engine(device).gather_rows(img_dev.reshape(-1, 3), pix)
-            copied = torch.cuda.Event()
-            copied.record(side)
-        tgt.record_stream(main)
-        pix.record_stream(side)
-        target = (tgt, copied)
+        if getattr(opts, 'cache_images', True):
+            # SURVEY 8(f)-1, second half: the training images live on the device (uploaded the first time each one is used: 7.68 MB
+            # per 800x800 image, 768 MB for 100 views); a step only gathers its N_rays target pixels from the resident stack.
+            # (The reference re-uploads the whole image every step, train.py:37-38; opts.cache_images=False restores that, e.g.
+            # for callers that modify `images` in place between steps.)
+            target = get_engine(device).gather_rows(_resident_image(images, i_img, device), pix)
+        else:
+            img = images[i_img]
+            img = img if isinstance(img, torch.Tensor) else torch.from_numpy(img)
+            # H2D of the target image (train.py:37-38) and the gather of the selected pixels (rays.py:62) on a side stream:
+            # the target is only needed at the first loss, so both overlap ray generation and the coarse forward
+            main = torch.cuda.current_stream(device)
+            side = _side_stream(device)
+            pix_ready = torch.cuda.Event()
+            pix_ready.record(main)
+            with torch.cuda.stream(side):
+                img_dev = img.to(device=device, dtype=torch.float32, non_blocking=True)
+                side.wait_event(pix_ready)
+                tgt = get_engine(device).gather_rows(img_dev.reshape(-1, 3), pix)
+                copied = torch.cuda.Event()
+                copied.record(side)
+            tgt.record_stream(main)
+            pix.record_stream(side)
+            target = (tgt, copied)
         rays_o, rays_d = make_o_d_selected(img_w, img_h, gt_intrinsic, pose, pix, ndc=llff, near=1.)
     rays = torch.cat((rays_o, rays_d), dim=-1)
 
@@ -138,6 +186,8 @@ def train(idx, i_train, images, gt_cam_param, hw, model, criterion, posenc, opti
     if opts.idx_save and idx % opts.idx_save == 0 and idx > 0 and (dist_ctx is None or dist_ctx.rank == 0):   # train.py:105-114
         save_path = os.path.join(LOG_DIR, opts.exp_name)
         os.makedirs(save_path, exist_ok=True)
-        checkpoint = {'idx': idx, 'model_state_dict': model.state_dict(), 'optimizer_state_dict': optimizer.state_dict()}
+        from . import nerf_process
+        checkpoint = {'idx': idx, 'model_state_dict': model.state_dict(), 'optimizer_state_dict': optimizer.state_dict(),
+                      'nb_rng_counter': nerf_process.rng_state()}       # extra key (ignored by the reference's main.py:111-117)
         torch.save(checkpoint, os.path.join(save_path, opts.exp_name + '_{}.pth.tar'.format(idx)))
     return loss

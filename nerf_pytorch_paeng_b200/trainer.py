@@ -13,49 +13,114 @@ from . import nerf_process as NP
 from .engine import get_engine
 
 
-class FlatAdam:
-    """torch.optim.Adam(lr, betas=(0.9,0.999), eps=1e-8) (main.py:79-80) over the model's two flat
-    parameter buffers, one nb_adam_step launch per network."""
+class FlatAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(model.parameters(), lr, betas=(0.9,0.999), eps=1e-8) (main.py:79-80) as ONE nb_adam_step launch per
+    network over the model's two flat parameter / gradient buffers.
+
+    A real torch.optim.Optimizer: `param_groups` holds model.parameters() (so the reference's scheduler.py:6
+    CosineAnnealingWarmupRestarts(_LRScheduler) and main.py:82-90,161 work unchanged), and `state_dict()` / `load_state_dict()`
+    speak torch.optim.Adam's format (per-parameter 'step', 'exp_avg', 'exp_avg_sq', parameters indexed in model.parameters()
+    order) -- a checkpoint written by the reference (train.py:105-114) resumes here and vice versa (main.py:111-115).  The
+    per-parameter moments are views of two flat buffers per network."""
 
     def __init__(self, model, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
         self.model = model
-        self.lr, self.betas, self.eps = lr, betas, eps
         self.step_count = 0
-        self.state = {}
-        self.param_groups = [{'lr': lr}]          # so reference-style LR schedulers can poke ['lr']
+        self._flat_state = {}                     # id(net) -> (m, v) flat fp32 buffers
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None, capturable=False,
+                        differentiable=False, fused=None)
+        super().__init__(list(model.parameters()), defaults)
+
+    # ---- convenience mirrors of the single param group
+    @property
+    def lr(self):
+        return self.param_groups[0]['lr']
+
+    @property
+    def betas(self):
+        return self.param_groups[0]['betas']
+
+    @property
+    def eps(self):
+        return self.param_groups[0]['eps']
 
     def _nets(self):
         return (self.model.model_coarse, self.model.model_fine)
 
+    def _moments(self, net):
+        """Flat first/second-moment buffers of one network; self.state[p] holds views of them."""
+        flat = net.flat_params()
+        st = self._flat_state.get(id(net))
+        if st is None or st[0].shape != flat.shape or st[0].device != flat.device:
+            old = st
+            st = (torch.zeros_like(flat), torch.zeros_like(flat))
+            if old is not None and old[0].shape == flat.shape:          # the model moved to another device: keep the moments
+                st[0].copy_(old[0])
+                st[1].copy_(old[1])
+            self._flat_state[id(net)] = st
+            for p, (o, n, shape) in zip(net._plist, net.slices):
+                ps = self.state[p]
+                ps['exp_avg'] = st[0][o:o + n].view(shape)
+                ps['exp_avg_sq'] = st[1][o:o + n].view(shape)
+                ps.setdefault('step', torch.tensor(float(self.step_count)))
+        return st
+
     def zero_grad(self, set_to_none=False):
+        """Zeroes the flat gradient buffers (p.grad stay views of them; set_to_none is ignored on purpose)."""
         for net in self._nets():
             if net.flat_grad is not None:
                 net.flat_grad.zero_()
 
-    def step(self):
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
         self.step_count += 1
-        lr = self.param_groups[0]['lr']
+        g = self.param_groups[0]
         for net in self._nets():
             flat = net.flat_params()
             grad = net.bind_flat_grad()
-            eng = get_engine(flat.device)
-            st = self.state.get(id(net))
-            if st is None or st[0].shape != flat.shape or st[0].device != flat.device:
-                st = (torch.zeros_like(flat), torch.zeros_like(flat))
-                self.state[id(net)] = st
-            eng.adam_step(flat, grad, st[0], st[1], lr, self.step_count, self.betas[0], self.betas[1], self.eps)
+            m, v = self._moments(net)
+            get_engine(flat.device).adam_step(flat, grad, m, v, g['lr'], self.step_count, g['betas'][0], g['betas'][1], g['eps'])
             net.mark_weights_changed()
+        return loss
 
     def state_dict(self):
-        return {'step': self.step_count, 'lr': self.param_groups[0]['lr'],
-                'state': [tuple(t.clone() for t in self.state[id(n)]) if id(n) in self.state else None for n in self._nets()]}
+        """torch.optim.Adam's layout: {'state': {i: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]}."""
+        if self.step_count > 0:
+            for net in self._nets():
+                self._moments(net)
+            for ps in self.state.values():
+                ps['step'] = torch.tensor(float(self.step_count))
+        return super().state_dict()
 
-    def load_state_dict(self, sd):
-        self.step_count = sd['step']
-        self.param_groups[0]['lr'] = sd['lr']
-        for n, st in zip(self._nets(), sd['state']):
-            if st is not None:
-                self.state[id(n)] = tuple(t.clone() for t in st)
+    def load_state_dict(self, state_dict):
+        """Accepts a torch.optim.Adam state_dict over model.parameters() (the reference's 'optimizer_state_dict',
+        main.py:115) or one written by this class."""
+        if 'param_groups' not in state_dict and 'step' in state_dict and 'state' in state_dict:     # round-1 format of this class
+            self.step_count = int(state_dict['step'])
+            self.param_groups[0]['lr'] = state_dict['lr']
+            for net, st in zip(self._nets(), state_dict['state']):
+                if st is not None:
+                    m, v = self._moments(net)
+                    m.copy_(st[0])
+                    v.copy_(st[1])
+            return
+        super().load_state_dict(state_dict)               # per-parameter tensors, cast to the parameters' device / dtype
+        steps = [float(ps['step']) for ps in self.state.values() if 'step' in ps]
+        self.step_count = int(max(steps)) if steps else 0
+        loaded = {p: dict(ps) for p, ps in self.state.items()}
+        self._flat_state = {}
+        for net in self._nets():
+            net.flat_params()
+            m, v = self._moments(net)                     # rebinds self.state[p] to views of fresh flat buffers
+            for p, (o, n, shape) in zip(net._plist, net.slices):
+                src = loaded.get(p)
+                if src is not None and 'exp_avg' in src:
+                    m[o:o + n].copy_(src['exp_avg'].reshape(-1))
+                    v[o:o + n].copy_(src['exp_avg_sq'].reshape(-1))
 
 
 MAX_POINTS_PER_PASS = 6 * 1024 * 1024      # activation stash + dY workspace ~ 10 KB/point (bf16) -> ~60 GB per pass at most
@@ -199,6 +264,9 @@ def render_frame(model, H, W, K, pose, opts, dist_ctx=None, chunk=None):
     # chunk_rays is a memory knob of the reference (nerf_process.py:236); the fused kernels hold no [n_pts,90]
     # tensor, so frames are rendered in larger chunks unless the caller pins `chunk`
     chunk = chunk or max(int(opts.chunk_rays), 65536)
+    if model.model_fine.precision != NP.NB_BF16:
+        # the fp32 parity path materialises every layer's [points, W] activations (~2.4 KB/point of workspace): keep a pass at <= 4M points
+        chunk = min(chunk, max(int(opts.chunk_rays), (4 << 20) // (opts.N_samples_c + max(opts.N_samples_f, 0))))
     rgb = eng.empty(hi - lo, 3)
     disp = eng.empty(hi - lo)
     ndc = opts.data_type == 'llff'
@@ -250,3 +318,76 @@ def render_rays_fused(model, rays, opts):
     if use_fine:
         out['rgb_f'], out['disp_f'] = rgb_f, disp_f
     return out
+
+
+class GraphedTrainStep:
+    """render + MSE_c + MSE_f + backward of both networks (the nb_train_rays call: 14 kernel launches, 2 memsets,
+    3 small copies) captured ONCE as a CUDA graph and replayed per step.  Nothing the graph needs changes on the host between
+    replays: the ray batch and targets are copied into static buffers, the loss lands in a static buffer, and the Philox counters of
+    the stratified / inverse-CDF draws are read from a device-resident counter that a captured nb_counter_add advances.  The Adam
+    update (whose learning rate and bias corrections are host scalars owned by the caller's scheduler) and the bf16 weight re-pack
+    stay ordinary launches after the replay.  Single-GPU path; data-parallel steps use trainer.train_step."""
+
+    def __init__(self, model, opts, n_rays, device):
+        self.model, self.opts, self.n = model, opts, int(n_rays)
+        self.eng = get_engine(device)
+        dev = self.eng.device
+        self.rays = torch.zeros(self.n, 6, device=dev)
+        self.target = torch.zeros(self.n, 3, device=dev)
+        self.loss = torch.zeros(2, device=dev)
+        self.ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.out = {}
+        self.graph = None
+        nc, nf = model.model_coarse, model.model_fine
+        if nc.precision != nf.precision or opts.N_samples_f <= 0 or getattr(opts, 'rng', None) is not None:
+            raise ValueError('GraphedTrainStep needs both networks in one precision, N_samples_f > 0 and in-kernel Philox draws')
+        self._per_step = self.n * opts.N_samples_c // 4 + 1 + self.n * opts.N_samples_f // 4 + 1
+
+    def _enqueue(self):
+        nc, nf = self.model.model_coarse, self.model.model_fine
+        nets = ((nc.flat, nc._packed), (nf.flat, nf._packed))
+        grads = (nc.flat_grad, nf.flat_grad)
+        args = NP._fused_sampling_args(self.n, self.opts, self.rays.device)
+        args['offset_c'], args['offset_f'] = 0, self.n * self.opts.N_samples_c // 4 + 1     # relative to the device counter
+        self.loss.zero_()
+        self.eng.train_rays(nc.desc, nets, grads, self.rays, self.target, self.n, precision=nc.precision, loss_buf=self.loss, out=self.out,
+                            which=3, ctr=self.ctr, **args)
+        self.eng.counter_add(self.ctr, self._per_step)
+
+    def capture(self):
+        nc, nf = self.model.model_coarse, self.model.model_fine
+        for net in (nc, nf):
+            net.flat_params()
+            net.packed_weights()
+            net.bind_flat_grad()
+        side = torch.cuda.Stream(device=self.rays.device)
+        side.wait_stream(torch.cuda.current_stream(self.rays.device))
+        with torch.cuda.stream(side):           # warm-up outside capture: workspace growth, function attributes, output tensors
+            for _ in range(2):
+                self._enqueue()
+        torch.cuda.current_stream(self.rays.device).wait_stream(side)
+        torch.cuda.synchronize(self.rays.device)
+        self._ptrs = (nc.flat.data_ptr(), nf.flat.data_ptr(), nc.flat_grad.data_ptr(), nf.flat_grad.data_ptr(), nc._packed.data_ptr(),
+                      nf._packed.data_ptr(), self.eng._fws.data_ptr())
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue()
+        return self
+
+    def _still_valid(self):
+        nc, nf = self.model.model_coarse, self.model.model_fine
+        return (nc.flat is not None and nc.flat_grad is not None and nc._packed is not None and self.eng._fws is not None
+                and self._ptrs == (nc.flat.data_ptr(), nf.flat.data_ptr(), nc.flat_grad.data_ptr(), nf.flat_grad.data_ptr(),
+                                   nc._packed.data_ptr(), nf._packed.data_ptr(), self.eng._fws.data_ptr()))
+
+    def __call__(self, optimizer, rays, target):
+        """One optimisation step; returns the static device tensor [loss_c, loss_f] (overwritten by the next call)."""
+        if self.graph is None or not self._still_valid():       # buffers were re-allocated (e.g. .to(), a larger workspace): re-capture
+            self.capture()
+        for net in (self.model.model_coarse, self.model.model_fine):
+            net.packed_weights()                                 # re-pack after the previous optimizer step (ordinary launch)
+        self.rays.copy_(rays, non_blocking=True)
+        self.target.copy_(target, non_blocking=True)
+        self.graph.replay()
+        optimizer.step()
+        return self.loss

@@ -140,6 +140,9 @@ def test_test_and_render_entries():
     net = NeRF(8, 256, 63, 27, [4], gt_camera_param=(K, poses)).cuda().set_precision('bf16')
     opts = make_opts(exp_name='nonexistent_ckpt')
     imgs = [np.random.rand(H, W, 3).astype(np.float32) for _ in range(2)]
+    with pytest.raises(FileNotFoundError):          # like the reference (test.py:20-21), a missing checkpoint is an error
+        test_mod.test(0, [0, 1], None, net, imgs, K, poses, (H, W), opts, save=False)
+    opts.allow_missing_checkpoint = True
     res = test_mod.test(0, [0, 1], None, net, imgs, K, poses, (H, W), opts, save=False)
     assert len(res['frames']) == 2 and res['frames'][0].shape == (H, W, 3) and res['frames'][0].dtype == np.uint8
     assert np.isfinite(res['psnr']).all()
@@ -430,7 +433,7 @@ def test_fused_driver_rejects_small_workspace():
     dev = torch.device('cuda', 0)
     eng = get_engine(dev)
     m = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).to(dev).model_coarse
-    cfg = RenderCfg(64, 128, NB_BF16, 2, 0, 0, 0)
+    cfg = RenderCfg(64, 128, NB_BF16, 2, 0, 0, 0, 0, None)
     need = C.c_size_t()
     eng._call('nb_render_workspace_bytes', C.byref(m.desc), 256, C.byref(cfg), 0, C.byref(need))
     assert need.value > 256 * 192 * 16
@@ -504,7 +507,7 @@ def test_fused_driver_workspace_is_not_overrun():
     tgt = torch.rand(n, 3, device=dev)
     opts = make_opts()
     lower, span = NP._coarse_bins(opts, dev)
-    cfg = RenderCfg(64, 128, NB_BF16, 2, 9, 0, 100000)
+    cfg = RenderCfg(64, 128, NB_BF16, 2, 9, 0, 100000, 0, None)
     need = C.c_size_t()
     eng._call('nb_render_workspace_bytes', C.byref(nc.desc), n, C.byref(cfg), 1, C.byref(need))
     G = 4096
@@ -520,3 +523,82 @@ def test_fused_driver_workspace_is_not_overrun():
     assert bool((whole[:G] == 0x5A).all()) and bool((whole[G + need.value:] == 0x5A).all()), 'workspace guard band overwritten'
     assert torch.isfinite(loss).all() and float(loss.min()) > 0 and torch.isfinite(gc).all() and torch.isfinite(gf).all()
     assert float(gc.abs().max()) > 0 and float(gf.abs().max()) > 0 and torch.isfinite(rgb_f).all()
+
+
+def test_resume_from_reference_checkpoint():
+    """f4: a checkpoint WRITTEN BY THE REFERENCE (train.py:105-114, torch.optim.Adam state, 3 real reference steps; fixture from
+    oracle/make_golden.py::gen_checkpoint) is loaded the way main.py:111-117 resumes -- model.load_state_dict +
+    optimizer.load_state_dict, here into trainer.FlatAdam -- and ONE resumed train step on the recorded inputs lands on the
+    parameters the reference itself reached with its 4th step."""
+    from nerf_pytorch_paeng_b200 import train as train_mod, trainer
+    from nerf_pytorch_paeng_b200.model import NeRF
+    from conftest import GOLDEN
+    r = load_golden('ref_checkpoint_w64_resume.npz')
+    net = NeRF(8, 64, 63, 27, [4], gt_camera_param=(None, None)).cuda().set_precision('fp32')
+    opt = trainer.FlatAdam(net, lr=5e-4)
+    idx = train_mod.load_checkpoint(os.path.join(GOLDEN, 'ref_checkpoint_w64_3.pth.tar'), net, opt)
+    assert idx == 3 and opt.step_count == 3
+    assert abs(opt.param_groups[0]['lr'] - float(r['lr_resume'])) < 1e-12        # the schedule position travels in param_groups
+    before = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    opts = make_opts(rng={'t_rand': cu(r['in/t_rand']), 'u': cu(r['in/u'])})
+    rays = cu(np.concatenate([r['in/rays_o'], r['in/rays_d']], -1))
+    loss = trainer.train_step(net, opt, rays, cu(r['in/target']), opts)
+    torch.cuda.synchronize()
+    assert abs(float(loss.sum()) - float(r['in/loss'])) <= 1e-5
+    assert opt.step_count == 4
+    worst = moved = 0.
+    for k, v in net.state_dict().items():
+        ref = torch.from_numpy(r['a/' + k]).cuda()
+        worst = max(worst, float((v - ref).abs().max()))
+        moved = max(moved, float((ref - before[k]).abs().max()))
+    assert moved > 1e-5                      # the step did something
+    # ... and it is the reference's step: an Adam update is ~lr = 1.85e-4 per element; elements whose gradient is ~0 amplify the
+    # 1e-4-relative difference between two fp32 implementations of the gradient (update = lr * m / (sqrt(v) + eps))
+    assert worst <= 1e-5, worst
+    num = sum(float(((v - torch.from_numpy(r['a/' + k]).cuda()) ** 2).sum()) for k, v in net.state_dict().items())
+    den = sum(float(((torch.from_numpy(r['a/' + k]).cuda() - before[k]) ** 2).sum()) for k in before)
+    assert (num / den) ** 0.5 <= 1e-2, (num / den) ** 0.5     # whole-vector error of the UPDATE itself
+    # the optimizer state after the resumed step keeps torch.optim.Adam's layout
+    sd = opt.state_dict()
+    assert float(sd['state'][0]['step']) == 4.0 and sd['state'][47]['exp_avg'].shape == (3,)
+
+
+def test_cuda_graph_train_step_equals_eager():
+    """f2: the captured CUDA graph of the train step (device-resident Philox counter) computes the same losses and gradients
+    as the eagerly enqueued step, replay after replay, and trains."""
+    from nerf_pytorch_paeng_b200 import nerf_process as NP, trainer
+    from nerf_pytorch_paeng_b200.model import NeRF
+    g = load_golden('raygen.npz')
+    n = 1024
+    rs = np.random.RandomState(3)
+    rays = cu(np.concatenate([np.tile(g['rays_o8'][:1], (n, 1)), g['rays_d8'][:n]], -1))
+    targets = [cu(rs.rand(n, 3).astype(np.float32)) for _ in range(3)]
+    opts = make_opts(seed=11)
+    opts.cdf_order = 'cuda'
+
+    def fresh():
+        torch.manual_seed(0)
+        net = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).cuda().set_precision('bf16')
+        return net, trainer.FlatAdam(net, lr=5e-4)
+    # eager
+    net_e, opt_e = fresh()
+    NP.set_rng_state(0)
+    eager = []
+    for t in targets:
+        loss = trainer.train_step(net_e, opt_e, rays, t, opts).clone()
+        eager.append((loss, net_e.model_coarse.flat_grad.clone(), net_e.model_fine.flat_grad.clone()))
+    # graphed
+    net_g, opt_g = fresh()
+    gs = trainer.GraphedTrainStep(net_g, opts, n, torch.device('cuda', 0)).capture()
+    gs.ctr.zero_()                                    # the warm-up replays advanced the device counter
+    eng = gs.eng
+    for i, t in enumerate(targets):
+        before = eng.launch_count()
+        loss = gs(opt_g, rays, t).clone()
+        torch.cuda.synchronize()
+        l_e, gc_e, gf_e = eager[i]
+        assert torch.allclose(loss, l_e, rtol=1e-5, atol=1e-7), (i, loss, l_e)
+        for got, ref in ((net_g.model_coarse.flat_grad, gc_e), (net_g.model_fine.flat_grad, gf_e)):
+            assert float((got - ref).norm() / ref.norm()) <= (1e-5 if i == 0 else 1e-2), i      # later steps: Adam's sign-like first updates amplify atomics-order noise
+        assert eng.launch_count() - before <= 4       # host-side launches per step: 2 re-packs + 2 Adam (the rest is ONE graph launch)
+    assert int(gs.ctr) == 3 * gs._per_step

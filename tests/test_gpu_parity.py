@@ -78,8 +78,11 @@ def test_get_rays_np(eng):
     from nerf_pytorch_paeng_b200 import rays
     o, d = rays.get_rays_np(int(g['H']), int(g['W']), g['K'], g['pose'])
     assert isinstance(d, np.ndarray) and d.shape == g['np_rays_d'].shape
-    np.testing.assert_allclose(d, g['np_rays_d'], rtol=0, atol=2.4e-7)   # fp32 vs the reference's fp64: <= 1 ulp
-    assert np.array_equal(o, g['np_rays_o'])
+    assert str(d.dtype) == str(g['np_dtype']) == 'float64'               # NumPy >= 2 promotion
+    assert np.array_equal(d, g['np_rays_d'])                             # bit-exact with the reference's fp64 result
+    assert np.array_equal(o, g['np_rays_o']) and o.dtype == g['np_rays_o'].dtype
+    # the global-batch table of main.py:95-101 (stack -> float32) is therefore bit-identical too
+    assert np.array_equal(d.astype(np.float32), g['np_rays_d'].astype(np.float32))
 
 
 def test_ndc_bit_exact(eng):
@@ -474,3 +477,21 @@ def test_sample_pdf_merge_equals_torch_sort(sc, sf, sorted_zc):
     # Philox route: same property, and the draws do not depend on which lane owns which sample
     z_fine2, z_s2, _, _ = eng.sample_pdf(z, w, sf, seed=5, offset=123, want_samples=True)
     assert torch.equal(z_fine2, torch.sort(torch.cat([z, z_s2], -1), -1)[0])
+
+
+@pytest.mark.parametrize('rows', [24, 8512, 40000])
+def test_sample_pdf_torch_cuda_order_fixture(eng, rows):
+    """a7: with the default summation order (torch's CUDA order, cdf_rows) the kernel's cdf, bin indices and samples equal, bit
+    for bit, what the UNMODIFIED reference produced on a B200 (tests/golden/sample_pdf_cuda.npz, oracle/make_golden_cuda.py).
+    The fixture holds a subset of each call's rows; cdf_rows pins the regime of the original call."""
+    g = load_golden('sample_pdf_cuda.npz')
+    z, w = cu(g[f'n{rows}_z']), cu(g[f'n{rows}_w'])
+    u = torch.linspace(0., 1., steps=128, device='cuda')
+    z_f, zs, inds, cdf = eng.sample_pdf(z, w, 128, u=u, want_samples=True, want_inds=True, want_cdf=True, cdf_rows=rows)
+    assert np.array_equal(npy(cdf), g[f'n{rows}_cdf'])
+    assert int((npy(inds) != g[f'n{rows}_inds'].astype(np.int64)).sum()) == 0
+    assert np.array_equal(npy(zs), g[f'n{rows}_samples'])
+    assert np.array_equal(npy(z_f), np.sort(np.concatenate([g[f'n{rows}_z'], g[f'n{rows}_samples']], -1), -1))
+    # and against the oracle's restatement of the same order
+    o_zf, o_zs, o_inds = orc.fine_z(g[f'n{rows}_z'], g[f'n{rows}_w'], npy(u), order='cuda', rows=rows)
+    assert np.array_equal(npy(inds), o_inds) and np.array_equal(npy(z_f), o_zf)

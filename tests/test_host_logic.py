@@ -103,3 +103,44 @@ def test_world_size_2_gloo(tmp_path):
         assert torch.equal(d['gc'], torch.full((11,), 3.0)) and torch.equal(d['gf'], torch.full((11,), 30.0))
         assert torch.equal(d['full'], torch.arange(13, dtype=torch.float32)[:, None].repeat(1, 3))
         assert float(d['t']) == 1.0
+
+
+def test_flat_adam_is_a_torch_optimizer_with_adam_state_dict():
+    """FlatAdam vs the reference's optimizer contract (main.py:79-90,111-115; scheduler.py:6): a checkpoint WRITTEN BY THE
+    REFERENCE (tests/golden/ref_checkpoint_w64_3.pth.tar, oracle/make_golden.py::gen_checkpoint) loads, round-trips in
+    torch.optim.Adam's format, and LR schedulers accept the optimizer.  Host-side logic only (no compute)."""
+    import os
+    from conftest import GOLDEN
+    from nerf_pytorch_paeng_b200 import trainer
+    from nerf_pytorch_paeng_b200.model import NeRF
+    ck = torch.load(os.path.join(GOLDEN, 'ref_checkpoint_w64_3.pth.tar'), map_location='cpu')
+    assert set(ck) == {'idx', 'model_state_dict', 'optimizer_state_dict'} and ck['idx'] == 3       # train.py:107-109
+    net = NeRF(8, 64, 63, 27, [4], gt_camera_param=(None, None))
+    net.load_state_dict(ck['model_state_dict'])                                                    # strict: same keys / shapes
+    opt = trainer.FlatAdam(net, lr=5e-4)
+    assert isinstance(opt, torch.optim.Optimizer) and len(opt.param_groups) == 1 and len(opt.param_groups[0]['params']) == 48
+    opt.load_state_dict(ck['optimizer_state_dict'])
+    ref = ck['optimizer_state_dict']
+    assert opt.step_count == 3 and opt.param_groups[0]['lr'] == ref['param_groups'][0]['lr']
+    sd = opt.state_dict()
+    assert sd['param_groups'][0]['params'] == ref['param_groups'][0]['params'] and set(sd['state']) == set(ref['state'])
+    for i, st in ref['state'].items():
+        assert float(sd['state'][i]['step']) == float(st['step'])
+        assert torch.equal(sd['state'][i]['exp_avg'], st['exp_avg']) and torch.equal(sd['state'][i]['exp_avg_sq'], st['exp_avg_sq'])
+    # the moments are views of one flat buffer per network, in parameters() order
+    m, v = opt._flat_state[id(net.model_coarse)]
+    p0 = net.model_coarse._plist[0]
+    assert opt.state[p0]['exp_avg'].data_ptr() == m.data_ptr()
+    # and the other way: torch's own Adam accepts a FlatAdam state_dict (a reference main.py can resume our checkpoints)
+    a = torch.optim.Adam(net.parameters(), lr=5e-4, betas=(0.9, 0.999))
+    a.load_state_dict(sd)
+    assert torch.equal(a.state[p0]['exp_avg'], ref['state'][0]['exp_avg'])
+    # schedulers: torch's, and the reference's own CosineAnnealingWarmupRestarts when baseline/_ref is installed
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda e: 0.5)
+    assert abs(opt.param_groups[0]['lr'] - 0.5 * sched.base_lrs[0]) < 1e-12
+    from baseline import ref_shim
+    if ref_shim.available():
+        cos = ref_shim.import_reference().scheduler.CosineAnnealingWarmupRestarts(opt, first_cycle_steps=200001, cycle_mult=1., max_lr=5e-4,
+                                                                                  min_lr=5e-5, warmup_steps=10000)
+        assert abs(opt.param_groups[0]['lr'] - 5e-5) < 1e-12                                       # scheduler.py:48-52 init_lr
+        assert cos.optimizer is opt

@@ -224,3 +224,23 @@ def test_render_train_w256_random_init(tag):
         flat = np.concatenate([grads[k].reshape(-1) for k in orc.mlp_param_names()])
         rel = np.linalg.norm((flat - ref).astype(np.float64)) / np.linalg.norm(ref.astype(np.float64))
         assert rel <= 2e-3, (tag_n, rel)
+
+
+@pytest.mark.parametrize('rows', [24, 8512, 40000])
+def test_cdf_torch_cuda_order_vs_b200_fixture(rows):
+    """The oracle's restatement of torch.sum / torch.cumsum's CUDA summation order (ATen Reduce.cuh / ScanUtils.cuh) against vectors
+    the unmodified reference produced on a B200 (oracle/make_golden_cuda.py): row sums, cdf, bin indices and samples bit for bit."""
+    g = load_golden('sample_pdf_cuda.npz')
+    assert int(g[f'n{rows}_rows']) == rows
+    z, w = g[f'n{rows}_z'], g[f'n{rows}_w']
+    ww = (w[:, 1:-1] + np.float32(1e-5)).astype(np.float32)
+    assert np.array_equal(orc.aten_cuda_sum_lastdim(ww), g[f'n{rows}_sum'])
+    cdf = orc.pdf_to_cdf(w[:, 1:-1], order='cuda', rows=rows)
+    assert np.array_equal(cdf, g[f'n{rows}_cdf'])
+    u = orc.torch_linspace01(128)
+    _, zs, inds = orc.fine_z(z, w, u, order='cuda', rows=rows)
+    assert np.array_equal(inds, g[f'n{rows}_inds'].astype(np.int64))
+    assert np.array_equal(zs, g[f'n{rows}_samples'])
+    # the CPU order (fp64 accumulation) is a different function: it must NOT be silently identical
+    if rows > 100:
+        assert not np.array_equal(orc.pdf_to_cdf(w[:, 1:-1]), g[f'n{rows}_cdf'])
