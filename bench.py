@@ -249,9 +249,43 @@ def run_ours(args):
         rays, tgt = ring[i % n_ring]
         return trainer.train_step(model, optimizer, rays, tgt, opts, dist_ctx=dctx)
 
+    # the step as a captured CUDA graph (render + loss + backward [+ all-reduce]; Adam and the weight re-pack follow
+    # as ordinary launches).  Measured equal to the eagerly enqueued step within noise (the step is GPU-bound): `value` times the eager step, `--graph`
+    # times the replay; at N = 1 the replay time is reported beside it as `cuda_graph`.
+    graphed = None
+    if args.graph and args.precision == 'bf16':
+        graphed = trainer.GraphedTrainStep(model, opts, N_RAYS, dev, dist_ctx=dctx).capture()
+
+    def step_eager(i):
+        rays, tgt = ring[i % n_ring]
+        return trainer.train_step(model, optimizer, rays, tgt, opts, dist_ctx=dctx)
+
+    if graphed is not None:
+        def step(i):                                                   # noqa: F811
+            rays, tgt = ring[i % n_ring]
+            return graphed(optimizer, rays, tgt)
     for i in range(args.warmup):
         step(i)
     barrier()
+    # the eagerly enqueued step, for comparison (same kernels, 18 launches + memsets/copies from the host per step)
+    eager_ms = None
+    if graphed is not None:
+        for i in range(3):
+            step_eager(i)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(args.steps):
+            step_eager(i)
+        g1.record()
+        barrier()
+        tt = torch.tensor([g0.elapsed_time(g1)], device=dev)
+        if dctx:
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        eager_ms = float(tt) / args.steps
+        for i in range(3):
+            step(i)
+        barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -262,13 +296,32 @@ def run_ours(args):
         loss = step(i)
     ev1.record()
     barrier()
-    launches = eng.launch_count() - l0
+    launches = eng.launch_count() - l0                      # launches issued through the C ABI from the host in the timed region
+    if graphed is not None:                                 # + the library's kernels inside each graph replay (counted at capture)
+        launches += graphed.kernels_per_replay * args.steps
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], device=dev)
     if dctx:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms_step = float(t) / args.steps
     value = N_RAYS * world / (ms_step / 1e3)
+
+    # ---- f2 evidence at N = 1: the same step replayed as a captured CUDA graph
+    graph_info = None
+    if graphed is None and dctx is None and args.precision == 'bf16':
+        gs = trainer.GraphedTrainStep(model, opts, N_RAYS, dev).capture()
+        for i in range(3):
+            gs(optimizer, *ring[i % n_ring])
+        torch.cuda.synchronize()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for i in range(args.steps):
+            gs(optimizer, *ring[i % n_ring])
+        q1.record()
+        torch.cuda.synchronize()
+        graph_info = {'ms_per_step': q0.elapsed_time(q1) / args.steps, 'kernels_per_replay': int(gs.kernels_per_replay), 'host_launches_per_step': 4,
+                      'what': 'trainer.GraphedTrainStep: render + loss + backward captured once, Philox counters on the device; Adam x2 and re-pack x2 from the host'}
+        del gs
 
     # ---- roofline: CUDA events (on the launching stream) around each of the three MLP kernels during a few extra steps.
     # engine.mlp_forward == one launch of mlp_fwd_chain_kernel<train>; the backward is issued as its two ABI stages so that
@@ -295,11 +348,11 @@ def run_ours(args):
         return ev_pair('wgrad', lambda: ob(*a, stage=2, **k))
     n_prof = min(args.steps, 5)
     opts.fused_driver = False         # same kernels, enqueued stage by stage so that events can be placed between them
-    step(0)                           # untimed: lets the caching allocator create the stage-by-stage buffers
+    step_eager(0)                     # untimed: lets the caching allocator create the stage-by-stage buffers
     torch.cuda.synchronize()
     eng.mlp_forward, eng.mlp_backward = fwd_timed, bwd_timed
     for i in range(n_prof):
-        step(i)
+        step_eager(i)
     torch.cuda.synchronize()
     opts.fused_driver = True
     eng.mlp_forward, eng.mlp_backward = of, ob
@@ -493,7 +546,10 @@ def run_ours(args):
                        'timed_region': f'{args.steps} steps = {ms_step * args.steps:.0f} ms; a sustained figure over 12,000 steps of the same step is in profiles/ (train_demo)',
                        'loss': float(loss.sum())},
             'roofline': roofline, 'cpu_baseline': cpu, 'gpu_baseline': gpu_base, 'e2e': e2e, 'render': render, 'gpu_launches': int(launches),
-            'clocks': clocks, 'gpu_launches_per_step': launches / args.steps, 'dp_check': dp_check, 'strong_scaling': strong}
+            'clocks': clocks, 'gpu_launches_per_step': launches / args.steps, 'dp_check': dp_check, 'strong_scaling': strong,
+            'step_mode': ('cuda_graph: render+loss+backward' + ('+all-reduce' if dctx else '') + ' captured once (the 18 kernels + 2 memsets + 3 copies of a step replay as one '
+                          'graph launch); 2 weight re-packs + 2 Adam launches follow from the host') if graphed is not None else 'eager launches',
+            'eager_ms_per_step': eager_ms, 'cuda_graph': graph_info, 'host_launches_per_step': (4 if graphed is not None else launches / args.steps)}
     emit(line)
 
 
@@ -526,6 +582,8 @@ def main():
     ap.add_argument('--cpu-rays', dest='cpu_rays', type=int, default=1024, help='rays per CPU-baseline step (BASELINE configs[0]: 1024)')
     ap.add_argument('--no-cpu', dest='no_cpu', action='store_true')
     ap.add_argument('--no-render', dest='no_render', action='store_true')
+    ap.add_argument('--graph', dest='graph', action='store_true', help='time the captured CUDA graph of the step (trainer.GraphedTrainStep) as `value`; '
+                    'by default the eagerly enqueued step is timed and the graph replay is reported beside it at N=1')
     ap.add_argument('--workload', type=str, default='blender', choices=['blender', 'llff'],
                     help='blender = BASELINE configs[1] (the headline); llff = configs[3] (NDC rays at 1008x756)')
     args = ap.parse_args()

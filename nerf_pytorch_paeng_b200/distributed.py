@@ -73,6 +73,59 @@ class DistContext:
         return torch.cat([b[:hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
 
 
+class PeerGradExchange:
+    """Gradient exchange without a collective kernel: every rank PUSHES its flat gradient into
+    a slot of every peer's symmetric-memory buffer with plain device-to-device copies -- executed by the copy engines over
+    NVLink, so they run UNDER the persistent MLP kernels that own every SM (an NCCL kernel cannot: it waits for an SM) -- and
+    the sum over ranks is folded into Adam's load (nb_adam_step_sum, rank-ordered => bit-identical replicas).
+
+    Schedule of one step: the coarse network's backward finishes before the fine pass starts (nb_train_rays nets=1 then 2), so
+    its 2.4 MB gradient travels during the fine forward/backward; only the fine network's push and one cross-rank barrier are
+    exposed at the end of the step.  Receive buffers are double-buffered by step parity."""
+
+    def __init__(self, ctx, model):
+        import torch.distributed._symmetric_memory as symm
+        self.ctx = ctx
+        self.world, self.rank = ctx.world_size, ctx.rank
+        nets = (model.model_coarse, model.model_fine)
+        self.sizes = [n.flat_params().numel() for n in nets]
+        self.G = sum(self.sizes) + 2                                  # + the two losses
+        dev = nets[0].flat.device
+        self.buf = symm.empty(2 * self.world * self.G, dtype=torch.float32, device=dev)
+        self.buf.zero_()
+        group = ctx.group if ctx.group is not None else dist.group.WORLD
+        self.hdl = symm.rendezvous(self.buf, group.group_name if hasattr(group, 'group_name') else group)
+        self.peer = [self.hdl.get_buffer(r, (2, self.world, self.G), torch.float32) for r in range(self.world)]
+        self.local = self.peer[self.rank]
+        self.whole, self.loss = ctx.joint_grad_buffer(model)          # [grad_c | grad_f | loss_c, loss_f]
+        self.side = torch.cuda.Stream(device=dev)
+        self.step_parity = 0
+        torch.cuda.synchronize(dev)
+        self.hdl.barrier(channel=0)
+
+    def push(self, lo, hi):
+        """Start copying whole[lo:hi] into slot `rank` of every peer (side stream, after everything enqueued so far)."""
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            for k in range(1, self.world):
+                r = (self.rank + k) % self.world                      # staggered targets: no two ranks start on the same peer
+                self.peer[r][self.step_parity, self.rank, lo:hi].copy_(self.whole[lo:hi], non_blocking=True)
+
+    def finish(self):
+        """All pushes of this step have landed everywhere: barrier on the side stream, then the main stream waits for it.
+        Returns the rank-ordered list of gradient sources for nb_adam_step_sum (own buffer at own rank)."""
+        with torch.cuda.stream(self.side):
+            self.hdl.barrier(channel=0)
+            done = torch.cuda.Event()
+            done.record()
+        torch.cuda.current_stream().wait_event(done)
+        par = self.step_parity
+        self.step_parity ^= 1
+        return [self.whole if r == self.rank else self.local[par, r] for r in range(self.world)]
+
+
 def init_from_env(backend=None):
     """torchrun-style init (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT)."""
     import os

@@ -65,6 +65,20 @@ class FlatAdam(torch.optim.Optimizer):
                 ps.setdefault('step', torch.tensor(float(self.step_count)))
         return st
 
+    @torch.no_grad()
+    def step_summed(self, srcs, offsets):
+        """Data-parallel step with the gradient sum over ranks folded into the update: srcs = rank-ordered joint gradient buffers
+        [grad_coarse | grad_fine | losses] (distributed.PeerGradExchange.finish()), offsets = start of each network inside them."""
+        self.step_count += 1
+        g = self.param_groups[0]
+        for net, off in zip(self._nets(), offsets):
+            flat = net.flat_params()
+            grad = net.bind_flat_grad()
+            m, v = self._moments(net)
+            ptrs = [t.data_ptr() + 4 * off for t in srcs]
+            get_engine(flat.device).adam_step_sum(flat, grad, ptrs, m, v, g['lr'], self.step_count, g['betas'][0], g['betas'][1], g['eps'])
+            net.mark_weights_changed()
+
     def zero_grad(self, set_to_none=False):
         """Zeroes the flat gradient buffers (p.grad stay views of them; set_to_none is ignored on purpose)."""
         for net in self._nets():
@@ -228,13 +242,26 @@ def train_step(model, optimizer, rays, target, opts, dist_ctx=None):
 
     Data parallel (dist_ctx): every rank normalises by the global ray count, the two flat gradient buffers and the two
     losses live in one joint buffer and are summed by a single all-reduce.  NB_DP_MODE=overlap restores the earlier
-    schedule (coarse all-reduce launched before the fine pass, three collectives per step) for comparison."""
+    schedule (coarse all-reduce launched before the fine pass, three collectives per step) for comparison.  Default ('auto'): the
+    copy-engine exchange of distributed.PeerGradExchange ('peer'), else 'joint'."""
     n_global = rays.shape[0] * (dist_ctx.world_size if dist_ctx is not None else 1)
     if dist_ctx is None:
         out = render_losses_and_grads(model, rays, target, opts, n_global=n_global)
         optimizer.step()
         return out['loss_buf']
-    mode = os.environ.get('NB_DP_MODE', 'joint')
+    mode = os.environ.get('NB_DP_MODE', 'auto')
+    if mode == 'auto':        # copy-engine exchange when the optimizer can fold the sum (FlatAdam) and symmetric memory is available
+        mode = 'joint'
+        if isinstance(optimizer, FlatAdam) and rays.is_cuda and getattr(dist_ctx, '_peer_ok', True):
+            try:
+                if getattr(dist_ctx, '_peer_exchange', None) is None:
+                    from .distributed import PeerGradExchange
+                    dist_ctx._peer_exchange = PeerGradExchange(dist_ctx, model)
+                mode = 'peer'
+            except Exception as e:                       # no symmetric memory (e.g. gloo, no P2P): NCCL all-reduce of the joint buffer
+                dist_ctx._peer_ok = False
+                import warnings
+                warnings.warn(f'peer gradient exchange unavailable ({type(e).__name__}: {e}); using one all-reduce of the joint buffer')
     if mode == 'overlap':
         works = []
         out = render_losses_and_grads(model, rays, target, opts, n_global=n_global,
@@ -244,6 +271,29 @@ def train_step(model, optimizer, rays, target, opts, dist_ctx=None):
             w.wait()
         optimizer.step()
         return out['loss_buf']
+    if mode == 'peer' and isinstance(optimizer, FlatAdam):
+        # copy-engine pushes under the kernels + sum folded into Adam (distributed.PeerGradExchange)
+        px = getattr(dist_ctx, '_peer_exchange', None)
+        if px is None:
+            from .distributed import PeerGradExchange
+            px = dist_ctx._peer_exchange = PeerGradExchange(dist_ctx, model)
+        nc_sz = px.sizes[0]
+        px.loss.zero_()
+
+        def net_done(net):
+            if net is model.model_coarse:
+                px.push(0, nc_sz)                       # travels during the fine pass
+            else:
+                px.push(nc_sz, px.G)                    # fine gradient + the two losses
+        render_losses_and_grads(model, rays, target, opts, n_global=n_global, loss_buf=px.loss, on_net_done=net_done)
+        srcs = px.finish()
+        loss_local = px.loss.clone()
+        optimizer.step_summed(srcs, (0, nc_sz))
+        total = loss_local
+        for r, t in enumerate(srcs):
+            if r != px.rank:
+                total = total + t[px.G - 2:px.G]
+        return total
     whole, loss = dist_ctx.joint_grad_buffer(model)
     loss.zero_()
     render_losses_and_grads(model, rays, target, opts, n_global=n_global, loss_buf=loss)
@@ -326,15 +376,21 @@ class GraphedTrainStep:
     replays: the ray batch and targets are copied into static buffers, the loss lands in a static buffer, and the Philox counters of
     the stratified / inverse-CDF draws are read from a device-resident counter that a captured nb_counter_add advances.  The Adam
     update (whose learning rate and bias corrections are host scalars owned by the caller's scheduler) and the bf16 weight re-pack
-    stay ordinary launches after the replay.  Single-GPU path; data-parallel steps use trainer.train_step."""
+    stay ordinary launches after the replay.  With a dist_ctx the joint-buffer gradient all-reduce is part of the graph."""
 
-    def __init__(self, model, opts, n_rays, device):
+    def __init__(self, model, opts, n_rays, device, dist_ctx=None):
         self.model, self.opts, self.n = model, opts, int(n_rays)
         self.eng = get_engine(device)
         dev = self.eng.device
+        self.dist_ctx = dist_ctx
+        self.n_global = self.n * (dist_ctx.world_size if dist_ctx is not None else 1)
         self.rays = torch.zeros(self.n, 6, device=dev)
         self.target = torch.zeros(self.n, 3, device=dev)
-        self.loss = torch.zeros(2, device=dev)
+        self.whole = None
+        if dist_ctx is not None:       # data parallel: gradients + losses in one joint buffer, ONE captured all-reduce (NCCL is graph-capturable)
+            self.whole, self.loss = dist_ctx.joint_grad_buffer(model)
+        else:
+            self.loss = torch.zeros(2, device=dev)
         self.ctr = torch.zeros(1, dtype=torch.int64, device=dev)
         self.out = {}
         self.graph = None
@@ -350,9 +406,11 @@ class GraphedTrainStep:
         args = NP._fused_sampling_args(self.n, self.opts, self.rays.device)
         args['offset_c'], args['offset_f'] = 0, self.n * self.opts.N_samples_c // 4 + 1     # relative to the device counter
         self.loss.zero_()
-        self.eng.train_rays(nc.desc, nets, grads, self.rays, self.target, self.n, precision=nc.precision, loss_buf=self.loss, out=self.out,
+        self.eng.train_rays(nc.desc, nets, grads, self.rays, self.target, self.n_global, precision=nc.precision, loss_buf=self.loss, out=self.out,
                             which=3, ctr=self.ctr, **args)
         self.eng.counter_add(self.ctr, self._per_step)
+        if self.dist_ctx is not None:
+            self.dist_ctx.allreduce_(self.whole)
 
     def capture(self):
         nc, nf = self.model.model_coarse, self.model.model_fine
@@ -370,8 +428,10 @@ class GraphedTrainStep:
         self._ptrs = (nc.flat.data_ptr(), nf.flat.data_ptr(), nc.flat_grad.data_ptr(), nf.flat_grad.data_ptr(), nc._packed.data_ptr(),
                       nf._packed.data_ptr(), self.eng._fws.data_ptr())
         self.graph = torch.cuda.CUDAGraph()
+        k0 = self.eng.launch_count()
         with torch.cuda.graph(self.graph):
             self._enqueue()
+        self.kernels_per_replay = self.eng.launch_count() - k0      # kernels of this library inside the graph
         return self
 
     def _still_valid(self):

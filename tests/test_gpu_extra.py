@@ -207,6 +207,78 @@ def test_two_gpu_equals_one_gpu(tmp_path):
         assert float((d['rgb_f'] - out['rgb_f'].cpu()).abs().max()) <= 1e-5
 
 
+def _ddp_worker_modes(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import torch.distributed as dist
+    from nerf_pytorch_paeng_b200 import distributed, trainer
+    from nerf_pytorch_paeng_b200.model import NeRF
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world)
+    ctx = distributed.DistContext()
+    g = load_golden('raygen.npz')
+    n = 1024
+    rs = np.random.RandomState(1)
+    rays = np.concatenate([np.tile(g['rays_o8'][:1], (n, 1)), g['rays_d8'][:n]], -1).astype(np.float32)
+    lo, hi = ctx.shard_range(n)
+    dev = lambda a: torch.from_numpy(a[lo:hi].copy()).cuda()
+    steps = [(rs.rand(n, 3).astype(np.float32), rs.rand(n, 64).astype(np.float32), rs.rand(n, 128).astype(np.float32)) for _ in range(3)]
+    res = {}
+    for mode in ('joint', 'peer'):
+        os.environ['NB_DP_MODE'] = mode
+        torch.manual_seed(0)
+        net = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).cuda().set_precision('bf16')
+        opt = trainer.FlatAdam(net, lr=5e-4)
+        losses = []
+        for target, t_rand, u in steps:
+            opts = make_opts(gpu_ids=list(range(world)), rank=rank, rng={'t_rand': dev(t_rand), 'u': dev(u)})
+            losses.append(trainer.train_step(net, opt, dev(rays), dev(target), opts, dist_ctx=ctx).cpu())
+        torch.cuda.synchronize()
+        res[mode] = {'pc': net.model_coarse.flat.cpu(), 'pf': net.model_fine.flat.cpu(), 'gc': net.model_coarse.flat_grad.cpu(),
+                     'gf': net.model_fine.flat_grad.cpu(), 'loss': torch.stack(losses)}
+    torch.save(res, os.path.join(out_dir, f'm{rank}.pt'))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs >= 2 GPUs (gpurun --gpus 2)')
+def test_two_gpu_bf16_joint_and_peer_exchange(tmp_path):
+    """The benchmarked data-parallel routes on the bf16 path: NB_DP_MODE=joint (one NCCL all-reduce of the joint buffer) and
+    NB_DP_MODE=peer (copy-engine pushes + sum folded into Adam) give every rank the same gradients / losses / weights as each
+    other and as ONE GPU stepping on the concatenated batch."""
+    import torch.multiprocessing as mp
+    from nerf_pytorch_paeng_b200 import trainer
+    from nerf_pytorch_paeng_b200.model import NeRF
+    world, port = 2, 29900 + os.getpid() % 300
+    mp.spawn(_ddp_worker_modes, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    g = load_golden('raygen.npz')
+    n = 1024
+    rs = np.random.RandomState(1)
+    rays = np.concatenate([np.tile(g['rays_o8'][:1], (n, 1)), g['rays_d8'][:n]], -1).astype(np.float32)
+    steps = [(rs.rand(n, 3).astype(np.float32), rs.rand(n, 64).astype(np.float32), rs.rand(n, 128).astype(np.float32)) for _ in range(3)]
+    torch.manual_seed(0)
+    net = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).cuda().set_precision('bf16')
+    opt = trainer.FlatAdam(net, lr=5e-4)
+    losses = []
+    for i, (target, t_rand, u) in enumerate(steps):
+        opts = make_opts(rng={'t_rand': cu(t_rand), 'u': cu(u)})
+        losses.append(trainer.train_step(net, opt, cu(rays), cu(target), opts).cpu())
+        if i == 0:
+            g1 = (net.model_coarse.flat_grad.cpu().clone(), net.model_fine.flat_grad.cpu().clone())
+    one = {'gc': net.model_coarse.flat_grad.cpu(), 'gf': net.model_fine.flat_grad.cpu(), 'loss': torch.stack(losses)}
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    d = [torch.load(os.path.join(tmp_path, f'm{r}.pt')) for r in range(world)]
+    for mode in ('joint', 'peer'):
+        # replicas stay bit-identical (same summed gradient, same Adam) ...
+        assert torch.equal(d[0][mode]['pc'], d[1][mode]['pc']) and torch.equal(d[0][mode]['pf'], d[1][mode]['pf']), mode
+        # ... and equal the single-GPU run on the whole batch: first-step losses exactly comparable, later steps drift with Adam's
+        # sign-like early updates
+        assert float((d[0][mode]['loss'][0] - one['loss'][0]).abs().max()) <= 1e-5, mode
+        assert float((d[0][mode]['loss'] - one['loss']).abs().max()) <= 5e-3, mode
+    assert rel(d[0]['peer']['gc'], d[0]['joint']['gc']) <= 1e-2 and rel(d[0]['peer']['gf'], d[0]['joint']['gf']) <= 1e-2
+    assert float((d[0]['peer']['loss'] - d[0]['joint']['loss']).abs().max()) <= 1e-3
+
+
 def test_train_entry_global_batch():
     """train.py:25-32: the global-batch path (device-resident shuffled [N,3,3] ray/rgb table + GetterRayBatchIdx cursor)."""
     from nerf_pytorch_paeng_b200 import rays as rays_mod, train as train_mod, trainer
