@@ -3,23 +3,27 @@
 //
 // Replaces nerf_process.py:69-84 (points + positional encoding) and model/NeRF.py:33-52.
 //
-// One persistent CTA per SM, 320 threads, two 128-point tiles ("slots") in flight:
-//   warp 0      weight producer: streams the pre-swizzled bf16 weight blobs (32 KB = 256 out-features x 64
-//               in-features) from L2 into a 2-stage shared-memory ring with cp.async.bulk (TMA unit) + mbarrier.
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16) with A = the slot's
-//               activation tile in shared memory (K-major, 128B swizzle), B = the weight stage, D = the
-//               slot's 256 fp32 TMEM columns; tcgen05.commit releases the weight stage / signals the epilogue.
-//   warps 2-5   epilogue of slot 0, warps 6-9 epilogue of slot 1 (thread = one point): build the
-//               positional encoding of the point straight into the A-operand tile (K3 fused into the first
-//               GEMM's operand), then per layer tcgen05.ld the accumulators, add bias, ReLU, round to bf16
-//               and write the next layer's A tile in place; sigma and rgb heads are CUDA-core dot products
+// One persistent CTA per SM (launched as clusters of two that share the weight stream), 576 threads, two 128-point tiles
+// ("slots") in flight:
+//   warp 0      weight producer: streams the pre-swizzled bf16 weight blobs (32 KB = 256 out-features x 64 in-features) from L2
+//               into a 2-stage shared-memory ring with cp.async.bulk (TMA unit) + mbarrier; in the default cluster mode each CTA
+//               fetches half of every stage and multicasts it into both CTAs' rings.
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16) with A = the slot's activation tile in shared
+//               memory (K-major, 128B swizzle), B = the weight stage, D = the slot's 256 fp32 TMEM columns; tcgen05.commit
+//               releases the weight stage / signals the epilogue.
+//   warps 2-9   epilogue of slot 0, warps 10-17 epilogue of slot 1: two warps per TMEM lane quarter, one per half of the
+//               accumulator columns (thread = one point): build the positional encoding of the point straight into the
+//               A-operand tile (K3 fused into the first GEMM's operand), then per layer tcgen05.ld the accumulators, add bias,
+//               ReLU, round to bf16 and write the next layer's A tile in place; sigma and rgb heads are CUDA-core dot products
 //               on the fp32 accumulators; raw[N,S,4] is the only HBM write in inference.
 // While the epilogue of one slot runs, the tensor core works on the other slot (ping-pong).
 // Layer chain ("steps") per tile, K-blocks of 64:  0: PE63->256 | 1-4: 256->256 | 5: [PE63,256]->256 |
 // 6,7: 256->256 (+sigma head after 7) | 8: feature 256->256 (no ReLU) | 9: [feat256,PEd27]->128 (+rgb head).
 //
-// In training the bf16 A tiles (layer inputs) are additionally bulk-stored to HBM as 16 KB swizzled blobs
-// which the backward kernels (nb_mlp_tc_bwd.cu) consume directly as UMMA operands.
+// In training the bf16 layer inputs are additionally written to HBM STRAIGHT FROM THE EPILOGUE'S REGISTERS (the same packed words
+// that go to the shared-memory A tile), in the chunk-major blob layout of stash_off() (nb_tc_common.cuh): fully coalesced 16-byte
+// stores, no shared-memory read-back, no extra barrier.  The backward kernels (nb_mlp_tc_bwd.cu) consume those blobs directly as
+// MN-major UMMA operands.
 #include <stdlib.h>
 #include <cuda.h>
 #include "nb_mlp.h"
@@ -59,9 +63,6 @@ constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;        // + alignment slac
 
 constexpr int kThreads = 576;   // warp 0 producer, warp 1 MMA, 8 epilogue warps per slot (2 per TMEM lane quarter: column halves)
 constexpr int kEpiThreads = 256;
-// stash route (measured): per-thread 16-byte stores from registers are 3x slower, cp.async.bulk stores starve
-// the weight ring; the tile is copied shared->global by the epilogue threads after they released the MMA warp
-constexpr bool kDirectStash = false;
 constexpr int kBarEpi0 = 1;
 
 __constant__ TcSmall c_fw;   // small fp32 parameters of the network being run (see nb_mlp_tc.h)   // named barrier ids of the two epilogue groups
@@ -90,7 +91,8 @@ struct FwdParams {
 // Arguments are reduced in "turns": sin(2^k x) = sin(2 pi frac(2^k x / 2 pi)), exact power-of-two scaling,
 // so the fast sin.approx/cos.approx see |arg| <= pi (abs error ~1e-6, far below a bf16 ulp).
 template <int L>
-__device__ __forceinline__ void pe_row_to_smem(uint32_t row_addr, uint32_t r, float x, float y, float z, bool one_pad, int c_lo, int c_hi) {
+__device__ __forceinline__ void pe_row_to_smem(uint32_t row_addr, uint32_t r, float x, float y, float z, bool one_pad, int c_lo, int c_hi,
+                                               uint8_t* gblob = nullptr) {
   constexpr int NF = 3 + 6 * L;
   constexpr int NCH = (NF + 8) / 8;          // chunks that hold features (+ the optional 1.0 pad column)
   float e[NCH * 8];
@@ -119,12 +121,16 @@ __device__ __forceinline__ void pe_row_to_smem(uint32_t row_addr, uint32_t r, fl
       w0 = pack_bf16(e[c * 8 + 0], e[c * 8 + 1]); w1 = pack_bf16(e[c * 8 + 2], e[c * 8 + 3]);
       w2 = pack_bf16(e[c * 8 + 4], e[c * 8 + 5]); w3 = pack_bf16(e[c * 8 + 6], e[c * 8 + 7]);
     }
-    if (c >= c_lo && c < c_hi) st_shared_v4(row_addr + (((uint32_t)c ^ (r & 7u)) << 4), w0, w1, w2, w3);   // this thread's column half
+    if (c >= c_lo && c < c_hi) {                                                                           // this thread's column half
+      st_shared_v4(row_addr + (((uint32_t)c ^ (r & 7u)) << 4), w0, w1, w2, w3);
+      if (gblob != nullptr) st_global_na_v4(gblob + stash_off(r, (uint32_t)c), w0, w1, w2, w3);          // training stash (wgrad's X operand)
+    }
   }
 }
 
 // copy 64 bf16 features (cols [c0, c0+ncol) of a materialised fp32 embedding row) into a swizzled row
-__device__ __forceinline__ void emb_row_to_smem(uint32_t row_addr, uint32_t r, const float* src, int ncol, bool one_pad, int c_lo, int c_hi) {
+__device__ __forceinline__ void emb_row_to_smem(uint32_t row_addr, uint32_t r, const float* src, int ncol, bool one_pad, int c_lo, int c_hi,
+                                                uint8_t* gblob = nullptr) {
 #pragma unroll 1
   for (int c = c_lo; c < c_hi; ++c) {
     float v[8];
@@ -133,8 +139,9 @@ __device__ __forceinline__ void emb_row_to_smem(uint32_t row_addr, uint32_t r, c
       const int f = c * 8 + j;
       v[j] = f < ncol ? src[f] : ((one_pad && f == ncol) ? 1.0f : 0.0f);
     }
-    st_shared_v4(row_addr + (((uint32_t)c ^ (r & 7u)) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                 pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    const uint32_t w0 = pack_bf16(v[0], v[1]), w1 = pack_bf16(v[2], v[3]), w2 = pack_bf16(v[4], v[5]), w3 = pack_bf16(v[6], v[7]);
+    st_shared_v4(row_addr + (((uint32_t)c ^ (r & 7u)) << 4), w0, w1, w2, w3);
+    if (gblob != nullptr) st_global_na_v4(gblob + stash_off(r, (uint32_t)c), w0, w1, w2, w3);
   }
 }
 
@@ -198,11 +205,12 @@ __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begi
           w0 = pack_bf16_relu(v[j * 8 + 0], v[j * 8 + 1]); w1 = pack_bf16_relu(v[j * 8 + 2], v[j * 8 + 3]);
           w2 = pack_bf16_relu(v[j * 8 + 4], v[j * 8 + 5]); w3 = pack_bf16_relu(v[j * 8 + 6], v[j * 8 + 7]);
         }
-        if (!(p.abl & 4)) st_shared_v4(row_addr + ((c ^ (r & 7u)) << 4), w0, w1, w2, w3);
-        // training: the same 16 bytes go straight to the stash blob (same swizzled image).  Direct stores keep the
-        // TMA unit and the shared-memory read port free for the weight stream and the MMA operands.
-        if (TRAIN && kDirectStash && gdst != nullptr)
-          *reinterpret_cast<uint4*>(gdst + (size_t)(c32 >> 1) * kBlobBytes + r * 128u + ((c ^ (r & 7u)) << 4)) = make_uint4(w0, w1, w2, w3);
+        if (KIND != 2 && !(p.abl & 4)) st_shared_v4(row_addr + ((c ^ (r & 7u)) << 4), w0, w1, w2, w3);     // (the view layer feeds no further GEMM)
+        // training: the same 16 bytes go straight from the registers to the stash blob in the chunk-major layout (stash_off): the
+        // 32 lanes of the warp (consecutive points) write 512 contiguous bytes.  No shared-memory read-back, no barrier, and the
+        // TMA unit / shared-memory ports stay with the weight stream and the MMA operands.
+        if (TRAIN && gdst != nullptr)
+          st_global_na_v4(gdst + (size_t)(c32 >> 1) * kBlobBytes + stash_off(r, c), w0, w1, w2, w3);
       }
     }
   }
@@ -373,7 +381,6 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
     const int bar_id = kBarEpi0 + slot;
     const uint32_t a_ready_addr = CTA2 ? mapa_u32(b_aready + 8 * slot, 0) : 0u;   // the LEADER's barrier
     uint32_t par_acc = 0;
-    bool store_pending = false;                              // a bulk store issued by grp_tid 0 still reads smem
     long long pe_wait = 0, pe_body = 0, pe_pro = 0;
 
     for (long long it = 0; it < max_it; ++it) {
@@ -388,7 +395,8 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
       // ---- layer-0 operand: positional encoding of the point (K3 fused) ----
       float dirx = 0.f, diry = 0.f, dirz = 0.f;
       const long long t_p0 = clock64();
-      if (TRAIN && store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, kEpiThreads); store_pending = false; }
+      uint8_t* g_embx = (TRAIN && tile_ok && !(p.abl & 16)) ? p.stash + p.st.off_embx + (size_t)tile_st * kBlobBytes : nullptr;
+      uint8_t* g_embd = (TRAIN && tile_ok && !(p.abl & 16)) ? p.stash + p.st.off_embd + (size_t)tile_st * kBlobBytes : nullptr;
       if (p.x_emb == nullptr) {
         const long long ray = pc / p.S;
         const float* rr = p.rays + ray * 6;
@@ -396,16 +404,11 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
         const float ox = rr[0], oy = rr[1], oz = rr[2], dx = rr[3], dy = rr[4], dz = rr[5];
         const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
         dirx = dx * inv; diry = dy * inv; dirz = dz * inv;
-        pe_row_to_smem<10>(aux_base + r * 128u, r, fmaf(dx, zz, ox), fmaf(dy, zz, oy), fmaf(dz, zz, oz), false, half * 4, half * 4 + 4);
+        pe_row_to_smem<10>(aux_base + r * 128u, r, fmaf(dx, zz, ox), fmaf(dy, zz, oy), fmaf(dz, zz, oz), false, half * 4, half * 4 + 4, g_embx);
       } else {
-        emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x, 63, false, half * 4, half * 4 + 4);
+        emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x, 63, false, half * 4, half * 4 + 4, g_embx);
       }
       fence_proxy_async_smem();
-      if (TRAIN) {
-        named_bar_sync(bar_id, kEpiThreads);
-        if (grp_tid == 0 && tile_ok) { bulk_s2g(p.stash + p.st.off_embx + (size_t)tile_st * kBlobBytes, aux_base, kBlobBytes); bulk_commit(); }
-        store_pending = true;
-      }
       if (CTA2) mbar_arrive_cluster(a_ready_addr); else mbar_arrive(b_aready + 8 * slot);
       pe_pro += clock64() - t_p0;
 
@@ -417,7 +420,6 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
         mbar_wait(b_accready + 8 * slot, par_acc); par_acc ^= 1;
         tc_fence_after();
         { const long long t1 = clock64(); pe_wait += t1 - t_e0; t_e0 = t1; }
-        if (TRAIN && store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, kEpiThreads); store_pending = false; }
         // The chunk loop is deliberately NOT unrolled and is specialised per step kind: one 32-column body is
         // ~200 instructions (3 KB) and stays resident in the instruction cache across chunks, steps and tiles.  (A fully
         // unrolled epilogue streamed ~30 KB of code per step through the I-cache and ran 5x slower: stall_no_inst.)
@@ -429,7 +431,7 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
         const bool wmask = TRAIN && tile_ok;
         const int c0 = half * 4, c1 = half * 4 + 4;            // this warp's 128 of the 256 columns (64 of 128 at step 9)
         uint8_t* gdst = nullptr;
-        if (TRAIN && tile_ok) {
+        if (TRAIN && tile_ok && !(p.abl & 16)) {
           const size_t off = (s < 8 ? p.st.off_h[s] : (s == 8 ? p.st.off_feat : p.st.off_g));
           gdst = p.stash + off + (size_t)tile_st * (s == 9 ? 2u : 4u) * kBlobBytes;
         }
@@ -444,37 +446,14 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(scratch), "f"(rgb[0]), "f"(rgb[1]), "f"(rgb[2]), "f"(sigma) : "memory");
         if (s == 5) {
           // the step-9 operand needs PE(viewdir) in aux; aux (PE of the point) was last read by MMA step 5, now retired
-          if (p.x_emb == nullptr) pe_row_to_smem<4>(aux_base + r * 128u, r, dirx, diry, dirz, false, half * 4, half * 4 + 4);
-          else emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x + 63, 27, false, half * 4, half * 4 + 4);
+          if (p.x_emb == nullptr) pe_row_to_smem<4>(aux_base + r * 128u, r, dirx, diry, dirz, false, half * 4, half * 4 + 4, g_embd);
+          else emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x + 63, 27, false, half * 4, half * 4 + 4, g_embd);
         }
         fence_proxy_async_smem();
         tc_fence_before();
         pe_body += clock64() - t_e0;
         if (s < 9) {      // release the MMA warp first: it needs only every thread's own (fenced) stores, not the group barrier
           if (CTA2) mbar_arrive_cluster(a_ready_addr); else mbar_arrive(b_aready + 8 * slot);
-        }
-        if (TRAIN) {
-          named_bar_sync(bar_id, kEpiThreads);        // the whole A tile (both column halves) is in shared memory: stash copies may start
-          if (s == 5) {                               // PE(viewdir) tile for wgrad: one 16 KB bulk store per tile
-            if (grp_tid == 0 && tile_ok) { bulk_s2g(p.stash + p.st.off_embd + (size_t)tile_st * kBlobBytes, aux_base, kBlobBytes); bulk_commit(); }
-            store_pending = true;
-          }
-        }
-        if (TRAIN && gdst != nullptr) {
-          // Activation stash: the tile is copied shared -> global by the epilogue threads themselves, fully coalesced
-          // (512 contiguous bytes per warp instruction), AFTER the MMA warp has been released, i.e. in the time this group
-          // would otherwise spend waiting for its next accumulator.  (A cp.async.bulk store here made the weight loads
-          // queue behind 64 KB of TMA traffic per step: the MMA issuer then waited 45% of its time for weight stages.)
-          const uint32_t n16 = ((s == 9) ? 2u : 4u) * (kBlobBytes / 16u);
-          if (p.abl & 32) {           // experiment: TMA bulk store instead of the thread copy
-            if (grp_tid == 0) { bulk_s2g(gdst, act_base, n16 * 16u); bulk_commit(); }
-            store_pending = true;
-          } else if (!(p.abl & 16))
-          for (uint32_t i = (uint32_t)grp_tid; i < n16; i += kEpiThreads) {
-            uint4 w;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(act_base + i * 16u));
-            asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gdst + (size_t)i * 16u), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
-          }
         }
         if (s == 9) {
           named_bar_sync(bar_id, kEpiThreads);                  // scratch rows of the other column half are visible
@@ -487,7 +466,6 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
         }
       }
     }
-    if (TRAIN && store_pending && grp_tid == 0) bulk_wait_all0();
     if (p.prof && grp_tid == 0 && slot == 0) {
       long long* o = p.prof + (size_t)blockIdx.x * 8;
       o[4] = pe_wait; o[5] = pe_body; o[6] = pe_pro;

@@ -3,12 +3,14 @@
 #include <functional>
 #include "nb_mlp.h"
 
-constexpr uint32_t kBlobBytes = 16384;   // one K-block of a 128-point tile: 128 rows x 64 bf16, 128B-swizzled
+constexpr uint32_t kBlobBytes = 16384;   // one K-block of a 128-point tile: 128 points x 64 bf16 (shared memory: 128B-swizzled K-major rows;
+                                         // stash / dY blobs in HBM: chunk-major, stash_off() in nb_tc_common.cuh)
 constexpr int kFwdSteps = 10;
 constexpr uint32_t kMaskTileBytes = 9 * 128 * 32;   // per tile
 
-// Activation stash written by the training forward: per tensor, per tile, consecutive 16 KB blobs
-// (the exact shared-memory image, so backward kernels bulk-load them straight into UMMA operands).
+// Activation stash written by the training forward: per tensor, per tile, consecutive 16 KB blobs in the chunk-major layout
+// [point/64][feature/8][point%64][8 features] (written straight from the epilogue's registers with coalesced 16-byte stores;
+// each 8 KB half is a SWIZZLE_NONE MN-major UMMA operand, so the weight-gradient kernel bulk-loads them as they are).
 struct TcStash {
   size_t off_embx, off_embd;   // PE(x) 63(+1.0 pad) cols, PE(d) 27(+1.0 pad) cols : 1 blob / tile
   size_t off_h[8];             // post-ReLU trunk outputs h0..h7                   : 4 blobs / tile

@@ -4,13 +4,13 @@
 //  (1) dgrad chain  -- same structure as the forward chain (nb_mlp_tc.cu): per 128-point tile the gradient
 //      wrt each layer's pre-activation is produced by a chain of tcgen05 GEMMs  dY_l = (dY_{l+1} . W_{l+1}) * relu'(h_l)
 //      with dY living in shared memory / TMEM; the ReLU masks come from the forward's activation stash, and
-//      every dY tile is bulk-stored to HBM as swizzled blobs for (2).  Steps per tile:
+//      every dY tile is written to HBM straight from the epilogue's registers (chunk-major blobs, stash_off()) for (2).  Steps per tile:
 //        prologue  dg = (d_rgb . Wc) * (g > 0)                     (CUDA cores, K=3)
 //        0: dfeat = dg . Wd[:, :256]        1: dh7 = (dfeat . Wf + dsigma (x) Wsigma) * (h7 > 0)
 //        2..8: dh_{l-1} = (dh_l . W_l[:, skip cols]) * (h_{l-1} > 0)   for l = 7..1
-//  (2) wgrad -- dW_l = dY_l^T . X_l reduced over all points.  The stashed blobs ([128 points x 64 features],
-//      128B-swizzled) are exactly UMMA "MN-major" operands, so both A = dY_l and B = X_l are bulk-loaded and fed
-//      to tcgen05.mma without any transposition; the 256x256 fp32 accumulator of one weight matrix fills the
+//  (2) wgrad -- dW_l = dY_l^T . X_l reduced over all points.  The stashed blobs ([128 points x 64 features] in the chunk-major
+//      layout of stash_off(): [point/64][feature/8][point%64][8 features]) are exactly SWIZZLE_NONE "MN-major" UMMA operands, so
+//      both A = dY_l and B = X_l are bulk-loaded (8 KB half blobs) and fed to tcgen05.mma without any transposition; the 256x256 fp32 accumulator of one weight matrix fills the
 //      512 TMEM columns.  The 12 (layer, input-block) jobs form one line of work cut into equal-traffic slices, one per
 //      CTA (wgrad is HBM-bound: 85 operand blobs per tile, see wg_segment); the view layer's two input blocks share one
 //      job (second accumulator region) and the density head rides on the feature job's B operand; bias gradients are
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 mlp_dgrad_chain_kernel(const DgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t s_act = sbase + kOffAct, s_aux = sbase + kOffAux, s_w = sbase + kOffW, s_bar = sbase + kOffBar;
+  const uint32_t s_act = sbase + kOffAct, s_w = sbase + kOffW, s_bar = sbase + kOffBar;
   const uint32_t b_wfull = s_bar, b_wempty = s_bar + 16, b_aready = s_bar + 32, b_accready = s_bar + 48, s_tmem = s_bar + 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long n_tiles = (p.P + 127) / 128;
@@ -178,12 +178,9 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
     const int half = ((warp - 2) >> 2) & 1;              // column half of the tile this warp handles
     const uint32_t q = (uint32_t)warp & 3u;
     const uint32_t r = q * 32u + (uint32_t)lane;
-    const uint32_t act_base = s_act + slot * kActBytes, aux_base = s_aux + slot * kBlobBytes;
+    const uint32_t act_base = s_act + slot * kActBytes;
     const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + (uint32_t)slot * 256u;
-    const int grp_tid = threadIdx.x - (64 + slot * kEpi);
-    const int bar_id = 1 + slot;
     uint32_t par_acc = 0;
-    bool store_pending = false;
     for (long long it = 0; it < max_it; ++it) {
       if (unit_of(slot, it) >= n_units) break;
       const long long tile_raw = MC ? unit_of(slot, it) * 2 + rank : unit_of(slot, it);
@@ -200,7 +197,8 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
       const uint4 gm0 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)(8 * 2) * 128 * 4));       // mask of g: columns 0..63 in words x,y
       const uint4 gm1 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)(8 * 2 + 1) * 128 * 4));   //            columns 64..127
       const uint32_t gmw[4] = {gm0.x, gm0.y, gm1.x, gm1.y};
-      if (store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, kEpi); store_pending = false; }
+      uint8_t* g_dg = tile_ok ? p.ws + p.w.off_dg + (size_t)tile_ws * 2 * kBlobBytes : nullptr;
+      uint8_t* g_draw = tile_ok ? p.ws + p.w.off_draw + (size_t)tile_ws * 2 * kBlobBytes : nullptr;
 #pragma unroll 1
       for (int c = half * 8; c < half * 8 + 8; ++c) {      // dg columns of this half (one K-block)
         float v[8];
@@ -211,24 +209,21 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
           const uint32_t gmsel = (c & 8) ? ((c & 4) ? gmw[3] : gmw[2]) : ((c & 4) ? gmw[1] : gmw[0]);
           v[j] = ((gmsel >> (31 - (col & 31))) & 1u) ? 0.f : val;
         }
-        st_shared_v4(act_base + (uint32_t)(c >> 3) * kBlobBytes + sw128_chunk(r, (uint32_t)(c & 7)), pack_bf16(v[0], v[1]),
-                     pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        const uint32_t w0 = pack_bf16(v[0], v[1]), w1 = pack_bf16(v[2], v[3]), w2 = pack_bf16(v[4], v[5]), w3 = pack_bf16(v[6], v[7]);
+        st_shared_v4(act_base + (uint32_t)(c >> 3) * kBlobBytes + sw128_chunk(r, (uint32_t)(c & 7)), w0, w1, w2, w3);   // A operand of step 0
+        if (g_dg) st_global_na_v4(g_dg + (size_t)(c >> 3) * kBlobBytes + stash_off(r, (uint32_t)(c & 7)), w0, w1, w2, w3);   // wgrad operand
       }
+      // d_raw as a (mostly zero) 128-feature operand for the rgb-head wgrad job: features 0..3 of the first blob, written by half 0;
+      // half 1 zero-fills the second blob (two blobs so that M = 128 is addressable)
+      if (g_draw) {
 #pragma unroll
-      for (int c = half * 4; c < half * 4 + 4; ++c) {
-        uint32_t w0 = 0, w1 = 0;
-        if (c == 0) { w0 = pack_bf16(dr.x, dr.y); w1 = pack_bf16(dr.z, dr.w); }
-        st_shared_v4(aux_base + sw128_chunk(r, (uint32_t)c), w0, w1, 0u, 0u);
+        for (int c = 0; c < 8; ++c) {
+          uint32_t w0 = 0, w1 = 0;
+          if (half == 0 && c == 0) { w0 = pack_bf16(dr.x, dr.y); w1 = pack_bf16(dr.z, dr.w); }
+          st_global_na_v4(g_draw + (size_t)half * kBlobBytes + stash_off(r, (uint32_t)c), w0, w1, 0u, 0u);
+        }
       }
       fence_proxy_async_smem();
-      named_bar_sync(bar_id, kEpi);
-      if (grp_tid == 0 && tile_ok) {
-        bulk_s2g(p.ws + p.w.off_dg + (size_t)tile_ws * 2 * kBlobBytes, act_base, 2 * kBlobBytes);
-        bulk_s2g(p.ws + p.w.off_draw + (size_t)tile_ws * 2 * kBlobBytes, aux_base, kBlobBytes);
-        bulk_s2g(p.ws + p.w.off_draw + (size_t)tile_ws * 2 * kBlobBytes + kBlobBytes, aux_base, kBlobBytes);
-        bulk_commit();
-      }
-      store_pending = true;
       mbar_arrive(b_aready + 8 * slot);
 
 #pragma unroll 1
@@ -242,7 +237,7 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
         }
         mbar_wait(b_accready + 8 * slot, par_acc); par_acc ^= 1;
         tc_fence_after();
-        if (store_pending) { if (grp_tid == 0) bulk_wait_read0(); named_bar_sync(bar_id, kEpi); store_pending = false; }
+        uint8_t* gdst = tile_ok ? p.ws + ((b == 0) ? p.w.off_dfeat : p.w.off_dh[8 - b]) + (size_t)tile_ws * 4 * kBlobBytes : nullptr;
         // rolled on purpose: one 32-column body stays resident in the instruction cache (see nb_mlp_tc.cu)
 #pragma unroll 1
         for (int c32 = half * 4; c32 < half * 4 + 4; ++c32) {
@@ -267,27 +262,18 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t c = (uint32_t)((c32 & 1) * 4 + j);
-            st_shared_v4(row_addr + ((c ^ (r & 7u)) << 4), pack_bf16(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16(v[j * 8 + 2], v[j * 8 + 3]),
-                         pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
+            const uint32_t w0 = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]), w1 = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
+            const uint32_t w2 = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), w3 = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+            if (b < kBwdSteps - 1) st_shared_v4(row_addr + ((c ^ (r & 7u)) << 4), w0, w1, w2, w3);       // A operand of the next step
+            // dY tile -> workspace for wgrad, straight from the registers (chunk-major blob: 512 contiguous bytes per warp)
+            if (gdst) st_global_na_v4(gdst + (size_t)(c32 >> 1) * kBlobBytes + stash_off(r, c), w0, w1, w2, w3);
           }
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        if (b < kBwdSteps - 1) mbar_arrive(b_aready + 8 * slot);     // release the MMA warp first (own stores are fenced above)
-        named_bar_sync(bar_id, kEpi);                       // the whole dY tile is in shared memory: the copy-out may start
-        if (tile_ok) {
-          // dY tile -> workspace for wgrad: coalesced copy by the epilogue threads after the MMA warp has been released
-          // (a cp.async.bulk store here competes with the weight stream for the TMA unit, see nb_mlp_tc.cu)
-          uint8_t* gdst = p.ws + ((b == 0) ? p.w.off_dfeat : p.w.off_dh[8 - b]) + (size_t)tile_ws * 4 * kBlobBytes;
-          for (uint32_t i = (uint32_t)grp_tid; i < 4u * (kBlobBytes / 16u); i += (uint32_t)kEpi) {
-            uint4 w;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(act_base + i * 16u));
-            asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gdst + (size_t)i * 16u), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
-          }
-        }
+        if (b < kBwdSteps - 1) mbar_arrive(b_aready + 8 * slot);
       }
     }
-    if (store_pending && grp_tid == 0) bulk_wait_all0();
   }
   tc_fence_before();
   __syncthreads();
@@ -413,18 +399,20 @@ mlp_wgrad_kernel(const WgradParams p) {
           const uint32_t a_addr = sbase + stage * kWgStageBytes;
           const uint32_t b_addr = a_addr + (uint32_t)J.m_blk * 8192u;
           const uint32_t first = (u == u0) ? 0u : 1u;
+          // operands: half blobs [feature/8][64 points][8 features] laid end to end => atoms of 8 features every 1024 B (SBO),
+          // 8-point groups every 128 B (LBO), a K16 slice every 256 B; 128 output rows (one m_half) = 16 atoms = 16 KB further
           for (int mh = 0; mh < m_halves; ++mh) {
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16)      // 64 points per stage = 4 x K16
-              umma_ss(tmem_base + (uint32_t)mh * 256u, umma_desc(a_addr + (uint32_t)mh * 16384u + k16 * 2048u, 8192, 1024),
-                      umma_desc(b_addr + k16 * 2048u, 8192, 1024), idesc, (first | (uint32_t)k16) ? 1u : 0u);
+              umma_ss(tmem_base + (uint32_t)mh * 256u, umma_desc_mn_noswz(a_addr + (uint32_t)mh * 16384u + k16 * 256u, 128, 1024),
+                      umma_desc_mn_noswz(b_addr + k16 * 256u, 128, 1024), idesc, (first | (uint32_t)k16) ? 1u : 0u);
           }
           if (J.n2_blk > 0) {
             const uint32_t b2_addr = b_addr + (uint32_t)J.n_blk * 8192u;
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16)
-              umma_ss(tmem_base + 256u, umma_desc(a_addr + k16 * 2048u, 8192, 1024), umma_desc(b2_addr + k16 * 2048u, 8192, 1024), idesc2,
-                      (first | (uint32_t)k16) ? 1u : 0u);
+              umma_ss(tmem_base + 256u, umma_desc_mn_noswz(a_addr + k16 * 256u, 128, 1024), umma_desc_mn_noswz(b2_addr + k16 * 256u, 128, 1024),
+                      idesc2, (first | (uint32_t)k16) ? 1u : 0u);
           }
           umma_commit(b_empty + 8 * stage);
           if (u == u1 - 1) umma_commit(b_done);
@@ -436,20 +424,24 @@ mlp_wgrad_kernel(const WgradParams p) {
     }
   } else {
     // ---- column sums (bias gradients, density-head rider) from the staged operands, then the TMEM -> global flush ----
+    // staged operand = consecutive 1 KB atoms [64 points][8 features].  Eight consecutive lanes read 8 consecutive points of ONE atom
+    // (128 contiguous bytes: conflict-free), so a lane accumulates partial column sums over the points j, j+8, .. of its atoms; the
+    // eight partial sums are combined by shuffles once per job segment.
     const int t = threadIdx.x - 64;           // 0..127
-    const int chunk = t & 31;                 // 16-byte chunk = 8 consecutive feature columns: blob chunk>>3, chunk-in-row chunk&7
-    const uint32_t rg = (uint32_t)t >> 5;     // row group: points rg*16 .. rg*16+15 of the stage
+    const int j8 = t & 7;                     // point j8 + 8*i of the stage
+    const int q16 = t >> 3;                   // 16 groups of 8 lanes: group g owns atoms g and g+16
     const uint32_t q = (uint32_t)warp & 3u;   // TMEM lane quarter of this warp
     uint32_t stage = 0, phase = 0, seg = 0;
     for (int j = 0; j < p.n_jobs; ++j) {
       long long u0, u1;
       if (!wg_segment(p, j, lo, hi, n_units, u0, u1)) continue;
       const WgradJob& J = p.job[j];
-      const bool do_bias = J.bias_out != nullptr && chunk < 8 * J.m_blk;
-      const bool do_sig = J.sig_draw != nullptr;
-      float bs[8], sg[8], sgb = 0.f;
+      const int a_atoms = 8 * J.m_blk;                      // dY operand: 16 or 32 atoms
+      const bool do_bias = J.bias_out != nullptr;
+      const bool do_sig = J.sig_draw != nullptr;            // rider on the B operand (N = 256 = 32 atoms)
+      float bs[2][8], sg[2][8], sgb = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { bs[k] = 0.f; sg[k] = 0.f; }
+      for (int k = 0; k < 8; ++k) { bs[0][k] = bs[1][k] = 0.f; sg[0][k] = sg[1][k] = 0.f; }
       float ds_next = 0.f;
       if (do_sig && t < 64) { const long long pt = u0 * 64 + t; ds_next = pt < p.n_points ? J.sig_draw[pt * 4 + 3] : 0.f; }
       for (long long u = u0; u < u1; ++u) {
@@ -463,49 +455,81 @@ mlp_wgrad_kernel(const WgradParams p) {
         mbar_wait(b_full + 8 * stage, phase);
         const uint32_t st_base = sbase + stage * kWgStageBytes;
         if (do_bias) {
-          const uint32_t base = st_base + (uint32_t)(chunk >> 3) * 8192u;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int atom = q16 + 16 * h;
+            if (atom < a_atoms) {
+              const uint32_t base = st_base + (uint32_t)atom * 1024u + (uint32_t)j8 * 16u;
 #pragma unroll 4
-          for (uint32_t r = 0; r < 16; ++r) {
-            uint32_t w0, w1, w2, w3;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                         : "r"(base + sw128_chunk(rg * 16u + r, (uint32_t)chunk & 7u)));
-            bs[0] += __uint_as_float(w0 << 16); bs[1] += __uint_as_float(w0 & 0xFFFF0000u);
-            bs[2] += __uint_as_float(w1 << 16); bs[3] += __uint_as_float(w1 & 0xFFFF0000u);
-            bs[4] += __uint_as_float(w2 << 16); bs[5] += __uint_as_float(w2 & 0xFFFF0000u);
-            bs[6] += __uint_as_float(w3 << 16); bs[7] += __uint_as_float(w3 & 0xFFFF0000u);
+              for (uint32_t i = 0; i < 8; ++i) {
+                uint32_t w0, w1, w2, w3;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + i * 128u));
+                bs[h][0] += __uint_as_float(w0 << 16); bs[h][1] += __uint_as_float(w0 & 0xFFFF0000u);
+                bs[h][2] += __uint_as_float(w1 << 16); bs[h][3] += __uint_as_float(w1 & 0xFFFF0000u);
+                bs[h][4] += __uint_as_float(w2 << 16); bs[h][5] += __uint_as_float(w2 & 0xFFFF0000u);
+                bs[h][6] += __uint_as_float(w3 << 16); bs[h][7] += __uint_as_float(w3 & 0xFFFF0000u);
+              }
+            }
           }
         }
-        if (do_sig) {     // B operand (N = 256 = 32 chunks): every thread has a chunk
-          const uint32_t base = st_base + (uint32_t)(J.m_blk + (chunk >> 3)) * 8192u;
+        if (do_sig) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t base = st_base + (uint32_t)(a_atoms + q16 + 16 * h) * 1024u + (uint32_t)j8 * 16u;
 #pragma unroll 4
-          for (uint32_t r = 0; r < 16; ++r) {
-            uint32_t w0, w1, w2, w3;
-            float ds;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                         : "r"(base + sw128_chunk(rg * 16u + r, (uint32_t)chunk & 7u)));
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ds) : "r"(sig + (rg * 16u + r) * 4u));
-            sg[0] = fmaf(ds, __uint_as_float(w0 << 16), sg[0]); sg[1] = fmaf(ds, __uint_as_float(w0 & 0xFFFF0000u), sg[1]);
-            sg[2] = fmaf(ds, __uint_as_float(w1 << 16), sg[2]); sg[3] = fmaf(ds, __uint_as_float(w1 & 0xFFFF0000u), sg[3]);
-            sg[4] = fmaf(ds, __uint_as_float(w2 << 16), sg[4]); sg[5] = fmaf(ds, __uint_as_float(w2 & 0xFFFF0000u), sg[5]);
-            sg[6] = fmaf(ds, __uint_as_float(w3 << 16), sg[6]); sg[7] = fmaf(ds, __uint_as_float(w3 & 0xFFFF0000u), sg[7]);
-            sgb += ds;
+            for (uint32_t i = 0; i < 8; ++i) {
+              uint32_t w0, w1, w2, w3;
+              float ds;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + i * 128u));
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ds) : "r"(sig + ((uint32_t)j8 + 8u * i) * 4u));
+              sg[h][0] = fmaf(ds, __uint_as_float(w0 << 16), sg[h][0]); sg[h][1] = fmaf(ds, __uint_as_float(w0 & 0xFFFF0000u), sg[h][1]);
+              sg[h][2] = fmaf(ds, __uint_as_float(w1 << 16), sg[h][2]); sg[h][3] = fmaf(ds, __uint_as_float(w1 & 0xFFFF0000u), sg[h][3]);
+              sg[h][4] = fmaf(ds, __uint_as_float(w2 << 16), sg[h][4]); sg[h][5] = fmaf(ds, __uint_as_float(w2 & 0xFFFF0000u), sg[h][5]);
+              sg[h][6] = fmaf(ds, __uint_as_float(w3 << 16), sg[h][6]); sg[h][7] = fmaf(ds, __uint_as_float(w3 & 0xFFFF0000u), sg[h][7]);
+              if (h == 0 && q16 == 0) sgb += ds;
+            }
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(b_empty + 8 * stage);
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
+      // combine the eight point-interleaved partial sums of every atom (lanes j8 = 0..7), then lane j8 adds column j8 of the atom
+      if (do_bias || do_sig) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              bs[h][k] += __shfl_xor_sync(0xffffffffu, bs[h][k], o);
+              sg[h][k] += __shfl_xor_sync(0xffffffffu, sg[h][k], o);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) sgb += __shfl_xor_sync(0xffffffffu, sgb, o);
+      }
       if (do_bias) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int col = chunk * 8 + k;
-          if (col >= J.m_first && col < J.m_valid) atomicAdd(J.bias_out + col - J.m_first, bs[k]);
+        for (int h = 0; h < 2; ++h) {
+          const int atom = q16 + 16 * h;
+          float mine = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) if (k == j8) mine = bs[h][k];
+          const int col = atom * 8 + j8;
+          if (atom < a_atoms && col >= J.m_first && col < J.m_valid) atomicAdd(J.bias_out + col - J.m_first, mine);
         }
       }
       if (do_sig) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) atomicAdd(J.sig_out + chunk * 8 + k, sg[k]);
-        if (chunk == 0) atomicAdd(J.sig_bias, sgb);
+        for (int h = 0; h < 2; ++h) {
+          float mine = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) if (k == j8) mine = sg[h][k];
+          atomicAdd(J.sig_out + (q16 + 16 * h) * 8 + j8, mine);
+        }
+        if (t == 0) atomicAdd(J.sig_bias, sgb);
       }
       // accumulators -> flat gradient
       mbar_wait(b_done, seg & 1);

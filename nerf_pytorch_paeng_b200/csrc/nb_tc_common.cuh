@@ -149,6 +149,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
 }
+// SWIZZLE_NONE ("interleave") MN-major operand: 16-byte atoms (8 bf16 of M/N) of 8 consecutive K rows are contiguous (128 B core
+// matrix); for this layout type the descriptor's SBO is the byte stride between atoms along M/N and LBO the stride between 8-row
+// groups along K (CUTLASS mma_traits_sm100.hpp, make_umma_desc<Major::MN>: ((1,n),(8,k)):((X,SBO),(1,LBO)) in uint128 units).
+__device__ __forceinline__ uint64_t umma_desc_mn_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
 // Instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major bit15, b_major bit16
 // (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major) {
@@ -212,5 +219,13 @@ __device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float 
       : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
 }
 __host__ __device__ __forceinline__ uint32_t sw128_chunk(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
+// Stash / dY blob layout in HBM (16 KB = 128 points x 64 features bf16): [half = point/64][chunk = feature/8][point%64][16 B].
+// A warp whose lanes are 32 consecutive points writes 512 contiguous bytes per chunk straight from registers, and a half blob
+// (8 KB, contiguous) is a SWIZZLE_NONE MN-major UMMA operand for the weight-gradient GEMMs: atoms of 8 features every 1024 B (SBO),
+// 8-point groups every 128 B (LBO).
+__host__ __device__ __forceinline__ uint32_t stash_off(uint32_t r, uint32_t c) { return (r >> 6) * 8192u + c * 1024u + (r & 63u) * 16u; }
+__device__ __forceinline__ void st_global_na_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 }  // namespace tc

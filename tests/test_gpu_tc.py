@@ -157,12 +157,10 @@ def flat_grads(eng, m, rays, z, d_raw, precision):
 
 
 def decode_blobs(buf, off, tiles, nblk):
-    """[tiles][nblk] swizzled 16 KB blobs (128 rows x 64 bf16) -> float32 [tiles*128, nblk*64]."""
-    raw = buf[off:off + tiles * nblk * 16384].view(np.uint16).reshape(tiles, nblk, 128, 8, 8)
-    r = np.arange(128)[:, None]
-    c = np.arange(8)[None, :]
-    un = raw[:, :, r, c ^ (r & 7), :]                      # [tiles, nblk, 128, 8 chunks, 8]
-    un = un.transpose(0, 2, 1, 3, 4).reshape(tiles * 128, nblk * 64)
+    """[tiles][nblk] 16 KB blobs in the chunk-major stash layout [point/64][feature/8][point%64][8 bf16] (stash_off in
+    nb_tc_common.cuh) -> float32 [tiles*128, nblk*64]."""
+    raw = buf[off:off + tiles * nblk * 16384].view(np.uint16).reshape(tiles, nblk, 2, 8, 64, 8)   # tile, blob, half, chunk, row, elem
+    un = raw.transpose(0, 2, 4, 1, 3, 5).reshape(tiles * 128, nblk * 64)                          # (tile, half, row), (blob, chunk, elem)
     return (un.astype(np.uint32) << 16).view(np.float32)
 
 
