@@ -7,16 +7,6 @@ import os
 LOG_DIR = os.path.join(os.path.abspath(os.path.dirname(os.path.realpath(__file__))), "logs")
 
 
-def str2bool(v):
-    if isinstance(v, bool):
-        return v
-    if v.lower() in ('yes', 'true', 't', 'y', '1'):
-        return True
-    if v.lower() in ('no', 'false', 'f', 'n', '0'):
-        return False
-    raise argparse.ArgumentTypeError('Boolean value expected.')
-
-
 def _config_file_args(path):
     out = []
     with open(path) as f:

@@ -99,9 +99,12 @@ def train(idx, i_train, images, gt_cam_param, hw, model, criterion, posenc, opti
     llff = opts.data_type == 'llff'
 
     if global_batch_idx is not None and opts.global_batch:                       # train.py:25-32
-        i_batch, rays_rgb, epoch = global_batch_idx(opts.N_rays)
-        batch = rays_rgb[i_batch - opts.N_rays:i_batch]
-        rays_o, rays_d, target = batch[:, 0].contiguous(), batch[:, 1].contiguous(), batch[:, 2].contiguous()
+        if hasattr(global_batch_idx, 'next_batch'):                              # device-native cursor (utils.GetterRayBatchIdx)
+            rays_o, rays_d, target = global_batch_idx.next_batch(opts.N_rays)
+        else:                                                                    # the reference's own getter object
+            i_batch, rays_rgb, epoch = global_batch_idx(opts.N_rays)
+            batch = rays_rgb[i_batch - opts.N_rays:i_batch]
+            rays_o, rays_d, target = batch[:, 0].contiguous(), batch[:, 1].contiguous(), batch[:, 2].contiguous()
         if llff:
             rays_o, rays_d = ndc_rays(img_h, img_w, float(gt_intrinsic[0][0]), 1., rays_o, rays_d)
     else:                                                                         # train.py:35-45

@@ -674,3 +674,23 @@ def test_cuda_graph_train_step_equals_eager():
             assert float((got - ref).norm() / ref.norm()) <= (1e-5 if i == 0 else 1e-2), i      # later steps: Adam's sign-like first updates amplify atomics-order noise
         assert eng.launch_count() - before <= 4       # host-side launches per step: 2 re-packs + 2 Adam (the rest is ONE graph launch)
     assert int(gs.ctr) == 3 * gs._per_step
+
+
+def test_batch_cursor_fast_path_equals_reference_protocol():
+    """utils.GetterRayBatchIdx: next_batch() (composed permutation + row gather, table never rewritten) walks the same batches as
+    the reference's protocol (utils.py:41-58 + the slice of train.py:29) across several reshuffles."""
+    from nerf_pytorch_paeng_b200.utils import GetterRayBatchIdx
+    n, bs = 1000, 96
+    table = torch.arange(n * 9, dtype=torch.float32, device='cuda').view(n, 3, 3)
+    torch.manual_seed(5)
+    a = GetterRayBatchIdx(table.clone())
+    ref = []
+    for _ in range(40):
+        i, t, ep = a(bs)
+        ref.append((t[i - bs:i].clone(), ep))
+    torch.manual_seed(5)
+    b = GetterRayBatchIdx(table.clone())
+    for k in range(40):
+        o, d, c = b.next_batch(bs)
+        assert torch.equal(torch.stack([o, d, c], 1), ref[k][0]) and b.epoch == ref[k][1], k
+    assert b.epoch == 3 and torch.equal(b.rays_rgb, table)          # three reshuffles, the table itself untouched
