@@ -98,7 +98,8 @@ class PeerGradExchange:
         self.peer = [self.hdl.get_buffer(r, (2, self.world, self.G), torch.float32) for r in range(self.world)]
         self.local = self.peer[self.rank]
         self.whole, self.loss = ctx.joint_grad_buffer(model)          # [grad_c | grad_f | loss_c, loss_f]
-        self.side = torch.cuda.Stream(device=dev)
+        self.sides = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(4, self.world - 1)))]   # several copy engines at once
+        self.side = self.sides[0]
         self.step_parity = 0
         torch.cuda.synchronize(dev)
         self.hdl.barrier(channel=0)
@@ -107,15 +108,20 @@ class PeerGradExchange:
         """Start copying whole[lo:hi] into slot `rank` of every peer (side stream, after everything enqueued so far)."""
         ev = torch.cuda.Event()
         ev.record()
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(ev)
-            for k in range(1, self.world):
-                r = (self.rank + k) % self.world                      # staggered targets: no two ranks start on the same peer
+        for st in self.sides:
+            st.wait_event(ev)
+        for k in range(1, self.world):
+            r = (self.rank + k) % self.world                          # staggered targets: no two ranks start on the same peer
+            with torch.cuda.stream(self.sides[(k - 1) % len(self.sides)]):
                 self.peer[r][self.step_parity, self.rank, lo:hi].copy_(self.whole[lo:hi], non_blocking=True)
 
     def finish(self):
         """All pushes of this step have landed everywhere: barrier on the side stream, then the main stream waits for it.
         Returns the rank-ordered list of gradient sources for nb_adam_step_sum (own buffer at own rank)."""
+        for st in self.sides[1:]:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            self.side.wait_event(ev)
         with torch.cuda.stream(self.side):
             self.hdl.barrier(channel=0)
             done = torch.cuda.Event()
