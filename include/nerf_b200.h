@@ -188,7 +188,7 @@ int nb_mlp_backward_stage(nb_handle_t h, const nb_mlp_desc* d, const float* para
                           void* ws, size_t ws_bytes, int32_t stage, void* stream);
 
 /* Diagnostic (NB_BF16): run the forward chain on rays/z and dump the raw fp32 TMEM accumulators of chain
- * step `step` (0..9; before bias/activation) to acc_out[N*S,256]; raw_out[N*S,4] as nb_mlp_forward_rays. */
+ * step `step` (0..8; before bias/activation; step 8 = the view layer with the feature layer folded in) to acc_out[N*S,256]; raw_out[N*S,4] as nb_mlp_forward_rays. */
 int nb_mlp_tc_probe(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t N, int32_t S,
                     const float* rays, const float* z, int32_t step, float* acc_out, float* raw_out, void* stream);
 

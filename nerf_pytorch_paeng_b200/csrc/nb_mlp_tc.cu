@@ -18,7 +18,13 @@
 //               on the fp32 accumulators; raw[N,S,4] is the only HBM write in inference.
 // While the epilogue of one slot runs, the tensor core works on the other slot (ping-pong).
 // Layer chain ("steps") per tile, K-blocks of 64:  0: PE63->256 | 1-4: 256->256 | 5: [PE63,256]->256 |
-// 6,7: 256->256 (+sigma head after 7) | 8: feature 256->256 (no ReLU) | 9: [feat256,PEd27]->128 (+rgb head).
+// 6,7: 256->256 (+sigma head after 7) | 8: view layer [h7 (256) through W', PEd27]->128 (+rgb head).
+// The reference's feature layer has NO activation (NeRF.py:44: feat = linear_feat(h)) and feeds only the view layer
+// (NeRF.py:47-49: relu(linear_d(cat[feat, d]))), so it is folded into the weights once per weight update (nb_tc_pack):
+//   W' = Wd[:, :256] . Wf  (128x256),  b' = Wd[:, :256] . b_feat + b_d,   g = relu(W' h7 + Wd[:, 256:] PE(d) + b')
+// which removes one 256x256 GEMM step per tile (11% of the network's MACs) from inference AND training; the backward
+// recovers the gradients of Wf, b_feat and Wd[:, :256] from G = dg^T h7 (nb_mlp_tc_bwd.cu).  The fp32 parity path keeps the
+// reference's explicit two-layer sequence.
 //
 // In training the bf16 layer inputs are additionally written to HBM STRAIGHT FROM THE EPILOGUE'S REGISTERS (the same packed words
 // that go to the shared-memory A tile), in the chunk-major blob layout of stash_off() (nb_tc_common.cuh): fully coalesced 16-byte
@@ -37,8 +43,8 @@ namespace {
 // ------------------------------------------------------------------------------------------
 // forward chain tables (D=8, W=256, skip=4, in_x=63, in_d=27)
 // ------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int fwd_nkb(int s) { return (s == 0) ? 1 : ((s == 5 || s == 9) ? 5 : 4); }
-__host__ __device__ constexpr int fwd_n(int s) { return s == 9 ? 128 : 256; }
+__host__ __device__ constexpr int fwd_nkb(int s) { return (s == 0) ? 1 : ((s == 5 || s == 8) ? 5 : 4); }
+__host__ __device__ constexpr int fwd_n(int s) { return s == 8 ? 128 : 256; }
 __host__ __device__ constexpr uint32_t fwd_blob_bytes(int s) { return (uint32_t)fwd_n(s) * 128u; }
 __host__ __device__ constexpr uint32_t fwd_w_off(int s) {   // byte offset of step s's first blob
   uint32_t o = 0;
@@ -49,7 +55,7 @@ __host__ __device__ constexpr uint32_t fwd_w_off(int s) {   // byte offset of st
 __host__ __device__ constexpr int fwd_a_src(int s, int kb) {
   if (s == 0) return -1;
   if (s == 5) return kb == 0 ? -1 : kb - 1;
-  if (s == 9) return kb == 4 ? -1 : kb;
+  if (s == 8) return kb == 4 ? -1 : kb;
   return kb;
 }
 
@@ -146,8 +152,8 @@ __device__ __forceinline__ void emb_row_to_smem(uint32_t row_addr, uint32_t r, c
 }
 
 // One layer's epilogue over `nchunks` groups of 32 accumulator columns (thread = one point / TMEM lane).
-// KIND 0: bias+ReLU -> bf16 A tile | 1: same + sigma head (step 7) | 2: view layer + rgb head (step 9; A tile only
-// written in training, for the stash) | 3: feature layer, no activation (step 8).
+// KIND 0: bias+ReLU -> bf16 A tile | 1: same + sigma head (step 7) | 2: view layer + rgb head (step 8; stored only in
+// training, for the stash).
 template <bool TRAIN, bool DBG, int KIND>
 __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begin, int c_end, uint32_t t_addr, uint32_t act_base, uint32_t r,
                                            long long pt, bool valid, uint32_t* mdst, uint8_t* gdst, float& sigma, float (&rgb)[3]) {
@@ -167,7 +173,7 @@ __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begi
     const float* bc = bias + c32 * 32;
 #pragma unroll
     for (int j = 0; j < 32; j += 2) add_f32x2(v[j], v[j + 1], bc[j], bc[j + 1]);      // packed FADD2: half the issue slots
-    if (TRAIN && KIND != 3) {
+    if (TRAIN) {
       // ReLU mask of this layer's output for the backward chain, one funnel shift per element: bit (31-j) of the
       // word = SIGN bit of column c32*32+j, i.e. set = inactive.  (An exact +0.0 pre-activation counts as active,
       // where torch's relu' is 0: a measure-zero difference.)  The (up to) four words of this thread's column half are
@@ -197,14 +203,8 @@ __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begi
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t c = (uint32_t)((c32 & 1) * 4 + j);
-        uint32_t w0, w1, w2, w3;
-        if (KIND == 3) {        // feature layer: no activation (NeRF.py:44)
-          w0 = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]); w1 = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
-          w2 = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]); w3 = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
-        } else {
-          w0 = pack_bf16_relu(v[j * 8 + 0], v[j * 8 + 1]); w1 = pack_bf16_relu(v[j * 8 + 2], v[j * 8 + 3]);
-          w2 = pack_bf16_relu(v[j * 8 + 4], v[j * 8 + 5]); w3 = pack_bf16_relu(v[j * 8 + 6], v[j * 8 + 7]);
-        }
+        const uint32_t w0 = pack_bf16_relu(v[j * 8 + 0], v[j * 8 + 1]), w1 = pack_bf16_relu(v[j * 8 + 2], v[j * 8 + 3]);
+        const uint32_t w2 = pack_bf16_relu(v[j * 8 + 4], v[j * 8 + 5]), w3 = pack_bf16_relu(v[j * 8 + 6], v[j * 8 + 7]);
         if (KIND != 2 && !(p.abl & 4)) st_shared_v4(row_addr + ((c ^ (r & 7u)) << 4), w0, w1, w2, w3);     // (the view layer feeds no further GEMM)
         // training: the same 16 bytes go straight from the registers to the stash blob in the chunk-major layout (stash_off): the
         // 32 lanes of the warp (consecutive points) write 512 contiguous bytes.  No shared-memory read-back, no barrier, and the
@@ -214,7 +214,7 @@ __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begi
       }
     }
   }
-  if (TRAIN && KIND != 3 && mdst != nullptr)
+  if (TRAIN && mdst != nullptr)
     asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(mdst), "r"(mw.x), "r"(mw.y), "r"(mw.z), "r"(mw.w) : "memory");
 }
 
@@ -423,39 +423,38 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
         // The chunk loop is deliberately NOT unrolled and is specialised per step kind: one 32-column body is
         // ~200 instructions (3 KB) and stays resident in the instruction cache across chunks, steps and tiles.  (A fully
         // unrolled epilogue streamed ~30 KB of code per step through the I-cache and ran 5x slower: stall_no_inst.)
-        const int kind = (s == 7) ? 1 : (s == 9 ? 2 : (s == 8 ? 3 : 0));
+        const int kind = (s == 7) ? 1 : (s == 8 ? 2 : 0);
         uint32_t* mdst = nullptr;
-        if (TRAIN && s != 8)
+        if (TRAIN)
           mdst = reinterpret_cast<uint32_t*>(p.stash + p.st.off_mask) +
                  ((((size_t)(tile_ok ? tile_st : 0) * 9 + (s < 8 ? s : 8)) * 2 + half) * 128 + r) * 4;     // [tile][9][half][row][4 words]
         const bool wmask = TRAIN && tile_ok;
-        const int c0 = half * 4, c1 = half * 4 + 4;            // this warp's 128 of the 256 columns (64 of 128 at step 9)
+        const int c0 = half * 4, c1 = half * 4 + 4;            // this warp's 128 of the 256 columns (64 of 128 in the view layer)
         uint8_t* gdst = nullptr;
         if (TRAIN && tile_ok && !(p.abl & 16)) {
-          const size_t off = (s < 8 ? p.st.off_h[s] : (s == 8 ? p.st.off_feat : p.st.off_g));
-          gdst = p.stash + off + (size_t)tile_st * (s == 9 ? 2u : 4u) * kBlobBytes;
+          const size_t off = (s < 8 ? p.st.off_h[s] : p.st.off_g);
+          gdst = p.stash + off + (size_t)tile_st * (s == 8 ? 2u : 4u) * kBlobBytes;
         }
         if (kind == 0) epi_chunks<TRAIN, DBG, 0>(p, s, c0, c1, t_addr, act_base, r, pt, valid, wmask ? mdst : nullptr, gdst, sigma, rgb);
         else if (kind == 1) epi_chunks<TRAIN, DBG, 1>(p, s, c0, c1, t_addr, act_base, r, pt, valid, wmask ? mdst : nullptr, gdst, sigma, rgb);
-        else if (kind == 2) epi_chunks<TRAIN, DBG, 2>(p, s, half * 2, half * 2 + 2, t_addr, act_base, r, pt, valid, wmask ? mdst : nullptr, gdst, sigma, rgb);
-        else epi_chunks<TRAIN, DBG, 3>(p, s, c0, c1, t_addr, act_base, r, pt, valid, nullptr, gdst, sigma, rgb);
+        else epi_chunks<TRAIN, DBG, 2>(p, s, half * 2, half * 2 + 2, t_addr, act_base, r, pt, valid, wmask ? mdst : nullptr, gdst, sigma, rgb);
         // heads: the two column halves of a row exchange their partial rgb / sigma sums through a scratch row in the
         // (now idle) fourth K-block of the activation tile
         const uint32_t scratch = act_base + 3u * kBlobBytes + r * 16u;
-        if (s == 9 && half == 1)
+        if (s == kFwdSteps - 1 && half == 1)
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(scratch), "f"(rgb[0]), "f"(rgb[1]), "f"(rgb[2]), "f"(sigma) : "memory");
         if (s == 5) {
-          // the step-9 operand needs PE(viewdir) in aux; aux (PE of the point) was last read by MMA step 5, now retired
+          // the view-layer operand needs PE(viewdir) in aux; aux (PE of the point) was last read by MMA step 5, now retired
           if (p.x_emb == nullptr) pe_row_to_smem<4>(aux_base + r * 128u, r, dirx, diry, dirz, false, half * 4, half * 4 + 4, g_embd);
           else emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x + 63, 27, false, half * 4, half * 4 + 4, g_embd);
         }
         fence_proxy_async_smem();
         tc_fence_before();
         pe_body += clock64() - t_e0;
-        if (s < 9) {      // release the MMA warp first: it needs only every thread's own (fenced) stores, not the group barrier
+        if (s < kFwdSteps - 1) {      // release the MMA warp first: it needs only every thread's own (fenced) stores, not the group barrier
           if (CTA2) mbar_arrive_cluster(a_ready_addr); else mbar_arrive(b_aready + 8 * slot);
         }
-        if (s == 9) {
+        if (s == kFwdSteps - 1) {
           named_bar_sync(bar_id, kEpiThreads);                  // scratch rows of the other column half are visible
           if (half == 0 && valid) {
             float4 o;
@@ -482,26 +481,46 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
 // ------------------------------------------------------------------------------------------
 struct BlobDesc {
   uint32_t dst_off;     // byte offset in the packed buffer
-  uint32_t src_off;     // float offset of W in the flat params
+  uint32_t src_off;     // float offset of W in the flat params (folded != 0: in the folded matrix W' of the packed buffer)
+  int folded;
   int ld;               // row stride (in-features) of W
   int transposed;       // 0: blob[n][k] = W[n0+n][k0+k]   1: blob[n][k] = W[k0+k][n0+n]
   int n0, k0;
   int n_rows;           // blob rows (128 or 256)
   int n_lim, k_lim;     // valid extents: n0+n < n_lim, k0+k < k_lim (else 0)
 };
-constexpr int kMaxBlobs = 80;
+constexpr int kMaxBlobs = 72;
 struct PackParams { BlobDesc b[kMaxBlobs]; int n; };
 
+// W'[n][k] = sum_j Wd[n][j] * Wf[j][k] (n < 128, k < 256; Wd row stride 283), b'[n] = sum_j Wd[n][j] * bf[j] + bd[n]: the
+// activation-free feature layer folded into the view layer, in fp32, once per weight update (8.4 MFLOP).
 __global__ void __launch_bounds__(256)
-pack_kernel(const PackParams pp, const float* __restrict__ prm, uint8_t* __restrict__ out, NbParamLayout L, uint32_t small_off) {
+fold_feat_kernel(const float* __restrict__ prm, NbParamLayout L, float* __restrict__ fold) {
+  const int n = blockIdx.x;            // 128 blocks: one output row each
+  const int k = threadIdx.x;           // 256 threads: one output column each
+  __shared__ float wd[256];
+  wd[k] = prm[L.wd + (size_t)n * 283 + k];
+  __syncthreads();
+  float acc = 0.f, accb = 0.f;
+#pragma unroll 8
+  for (int j = 0; j < 256; ++j) acc = fmaf(wd[j], prm[L.wf + (size_t)j * 256 + k], acc);
+  fold[(size_t)n * 256 + k] = acc;
+  if (k == 0) {
+    for (int j = 0; j < 256; ++j) accb = fmaf(wd[j], prm[L.bf + j], accb);
+    fold[128 * 256 + n] = accb + prm[L.bd + n];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pack_kernel(const PackParams pp, const float* __restrict__ prm, uint8_t* __restrict__ out, NbParamLayout L, uint32_t small_off,
+            const float* __restrict__ fold) {
   if ((int)blockIdx.y == pp.n) {       // last row of blocks: gather the small fp32 parameters (TcSmall)
     TcSmall* sm = reinterpret_cast<TcSmall*>(out + small_off);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 10 * 256; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kFwdSteps * 256; i += gridDim.x * blockDim.x) {
       const int s = i >> 8, c = i & 255;
       float v = 0.f;
       if (s < 8) v = prm[L.b[s] + c];
-      else if (s == 8) v = prm[L.bf + c];
-      else if (c < 128) v = prm[L.bd + c];
+      else if (c < 128) v = fold[128 * 256 + c];       // b' of the folded view layer
       sm->bias[s][c] = v;
       if (s == 0) sm->ws[c] = prm[L.ws + c];
       if (i < 384) sm->wc[i] = prm[L.wc + i];
@@ -520,7 +539,8 @@ pack_kernel(const PackParams pp, const float* __restrict__ prm, uint8_t* __restr
       const int k = c * 8 + j;
       const int gn = d.n0 + n, gk = d.k0 + k;
       float x = 0.f;
-      if (gn < d.n_lim && gk < d.k_lim) x = d.transposed ? prm[d.src_off + (size_t)gk * d.ld + gn] : prm[d.src_off + (size_t)gn * d.ld + gk];
+      const float* src = d.folded ? fold : prm;
+      if (gn < d.n_lim && gk < d.k_lim) x = d.transposed ? src[d.src_off + (size_t)gk * d.ld + gn] : src[d.src_off + (size_t)gn * d.ld + gk];
       v[j] = x;
     }
     uint4 w = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -528,9 +548,9 @@ pack_kernel(const PackParams pp, const float* __restrict__ prm, uint8_t* __restr
   }
 }
 
-void add_blob(PackParams& pp, uint32_t& off, size_t src, int ld, int tr, int n0, int k0, int rows, int n_lim, int k_lim) {
+void add_blob(PackParams& pp, uint32_t& off, size_t src, int ld, int tr, int n0, int k0, int rows, int n_lim, int k_lim, int folded = 0) {
   BlobDesc& b = pp.b[pp.n++];
-  b.dst_off = off; b.src_off = (uint32_t)src; b.ld = ld; b.transposed = tr; b.n0 = n0; b.k0 = k0; b.n_rows = rows;
+  b.dst_off = off; b.src_off = (uint32_t)src; b.folded = folded; b.ld = ld; b.transposed = tr; b.n0 = n0; b.k0 = k0; b.n_rows = rows;
   b.n_lim = n_lim; b.k_lim = k_lim;
   off += (uint32_t)rows * 128u;
 }
@@ -546,7 +566,8 @@ bool nb_tc_supported(const nb_mlp_desc& d) {
 
 size_t nb_tc_fwd_packed_bytes() { return fwd_w_off(kFwdSteps); }
 size_t nb_tc_small_offset() { return nb_tc_fwd_packed_bytes() + nb_tc_bwd_packed_bytes(); }
-size_t nb_tc_packed_bytes(const nb_mlp_desc&) { return nb_tc_small_offset() + sizeof(TcSmall); }
+size_t nb_tc_fold_offset() { return (nb_tc_small_offset() + sizeof(TcSmall) + 255) & ~(size_t)255; }
+size_t nb_tc_packed_bytes(const nb_mlp_desc&) { return nb_tc_fold_offset() + kFoldFloats * sizeof(float); }
 
 TcStash nb_tc_stash_layout(long long P) {
   TcStash s;
@@ -555,7 +576,6 @@ TcStash nb_tc_stash_layout(long long P) {
   s.off_embx = off; off += T * kBlobBytes;
   s.off_embd = off; off += T * kBlobBytes;
   for (int i = 0; i < 8; ++i) { s.off_h[i] = off; off += T * 4 * kBlobBytes; }
-  s.off_feat = off; off += T * 4 * kBlobBytes;
   s.off_g = off; off += T * 2 * kBlobBytes;
   s.off_mask = off; off += T * kMaskTileBytes;
   s.total = off;
@@ -577,17 +597,19 @@ int nb_tc_pack(nb_handle_t h, const nb_mlp_desc* d, const float* params, void* p
   add_blob(pp, off, L.w[5], 319, 0, 0, 0, 256, 256, 63);                                 // step 5: PE columns
   for (int kb = 0; kb < 4; ++kb) add_blob(pp, off, L.w[5] + 63, 319, 0, 0, 64 * kb, 256, 256, 256);
   for (int l = 6; l <= 7; ++l) for (int kb = 0; kb < 4; ++kb) add_blob(pp, off, L.w[l], 256, 0, 0, 64 * kb, 256, 256, 256);
-  for (int kb = 0; kb < 4; ++kb) add_blob(pp, off, L.wf, 256, 0, 0, 64 * kb, 256, 256, 256);
-  for (int kb = 0; kb < 4; ++kb) add_blob(pp, off, L.wd, 283, 0, 0, 64 * kb, 128, 128, 256);   // step 9: feature columns
+  for (int kb = 0; kb < 4; ++kb) add_blob(pp, off, 0, 256, 0, 0, 64 * kb, 128, 128, 256, 1);   // step 8: h7 columns through the folded W'
   add_blob(pp, off, L.wd + 256, 283, 0, 0, 0, 128, 128, 27);                                   //         view-dir PE columns
   if (off != nb_tc_fwd_packed_bytes()) { NB_SET_ERR(h, "nb_tc_pack: internal layout mismatch"); return NB_ERR_INVALID; }
   // ---- backward (dgrad) blobs: B = W^T
-  nb_tc_bwd_add_blobs(L, [&](size_t src, int ld, int tr, int n0, int k0, int rows, int n_lim, int k_lim) {
-    add_blob(pp, off, src, ld, tr, n0, k0, rows, n_lim, k_lim);
+  nb_tc_bwd_add_blobs(L, [&](size_t src, int ld, int tr, int n0, int k0, int rows, int n_lim, int k_lim, int folded) {
+    add_blob(pp, off, src, ld, tr, n0, k0, rows, n_lim, k_lim, folded);
   });
   if (pp.n > kMaxBlobs) { NB_SET_ERR(h, "nb_tc_pack: too many blobs"); return NB_ERR_INVALID; }
+  float* fold = reinterpret_cast<float*>((uint8_t*)packed + nb_tc_fold_offset());
+  fold_feat_kernel<<<128, 256, 0, st>>>(params, L, fold);
+  NB_LAUNCHED(h);
   dim3 grid(4, pp.n + 1);
-  pack_kernel<<<grid, 256, 0, st>>>(pp, params, (uint8_t*)packed, L, (uint32_t)nb_tc_small_offset());
+  pack_kernel<<<grid, 256, 0, st>>>(pp, params, (uint8_t*)packed, L, (uint32_t)nb_tc_small_offset(), fold);
   NB_LAUNCHED(h);
   return NB_OK;
 }

@@ -6,8 +6,8 @@
 //      with dY living in shared memory / TMEM; the ReLU masks come from the forward's activation stash, and
 //      every dY tile is written to HBM straight from the epilogue's registers (chunk-major blobs, stash_off()) for (2).  Steps per tile:
 //        prologue  dg = (d_rgb . Wc) * (g > 0)                     (CUDA cores, K=3)
-//        0: dfeat = dg . Wd[:, :256]        1: dh7 = (dfeat . Wf + dsigma (x) Wsigma) * (h7 > 0)
-//        2..8: dh_{l-1} = (dh_l . W_l[:, skip cols]) * (h_{l-1} > 0)   for l = 7..1
+//        0: dh7 = (dg . W' + dsigma (x) Wsigma) * (h7 > 0)          with the folded W' = Wd[:, :256] . Wf (nb_mlp_tc.cu)
+//        1..7: dh_{l-1} = (dh_l . W_l[:, skip cols]) * (h_{l-1} > 0)   for l = 7..1
 //  (2) wgrad -- dW_l = dY_l^T . X_l reduced over all points.  The stashed blobs ([128 points x 64 features] in the chunk-major
 //      layout of stash_off(): [point/64][feature/8][point%64][8 features]) are exactly SWIZZLE_NONE "MN-major" UMMA operands, so
 //      both A = dY_l and B = X_l are bulk-loaded (8 KB half blobs) and fed to tcgen05.mma without any transposition; the 256x256 fp32 accumulator of one weight matrix fills the
@@ -24,7 +24,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int kBwdSteps = 9;
+constexpr int kBwdSteps = 8;
 __host__ __device__ constexpr int bwd_nkb(int b) { return b == 0 ? 2 : 4; }
 __host__ __device__ constexpr uint32_t bwd_w_off(int b) {
   uint32_t o = 0;
@@ -36,7 +36,6 @@ __host__ __device__ constexpr uint32_t bwd_w_off(int b) {
 struct BwdWs {
   size_t off_draw;     // [T][2]  d_raw (cols 0..3) as a blob, stored twice: A operand (M=128) of the head wgrad jobs
   size_t off_dg;       // [T][2]
-  size_t off_dfeat;    // [T][4]
   size_t off_dh[8];    // [T][4]  dh0..dh7
   size_t total;
 };
@@ -46,7 +45,6 @@ BwdWs bwd_ws_layout(long long P) {
   size_t off = 0;
   w.off_draw = off; off += T * 2 * kBlobBytes;
   w.off_dg = off; off += T * 2 * kBlobBytes;
-  w.off_dfeat = off; off += T * 4 * kBlobBytes;
   for (int i = 0; i < 8; ++i) { w.off_dh[i] = off; off += T * 4 * kBlobBytes; }
   w.total = off;
   return w;
@@ -228,23 +226,23 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
 
 #pragma unroll 1
       for (int b = 0; b < kBwdSteps; ++b) {
-        // ReLU mask of h_{8-b} for this step (b >= 1): 8 words per row, fetched while the MMA runs
-        uint32_t mq[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};      // set bit = inactive unit
-        if (b >= 1) {
-          const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)((8 - b) * 2) * 128 * 4));
-          const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)((8 - b) * 2 + 1) * 128 * 4));
+        // ReLU mask of h_{7-b}, the layer whose pre-activation gradient this step produces: 8 words per row, fetched while the MMA runs
+        uint32_t mq[8];      // set bit = inactive unit
+        {
+          const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)((7 - b) * 2) * 128 * 4));
+          const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)((7 - b) * 2 + 1) * 128 * 4));
           mq[0] = m0.x; mq[1] = m0.y; mq[2] = m0.z; mq[3] = m0.w; mq[4] = m1.x; mq[5] = m1.y; mq[6] = m1.z; mq[7] = m1.w;
         }
         mbar_wait(b_accready + 8 * slot, par_acc); par_acc ^= 1;
         tc_fence_after();
-        uint8_t* gdst = tile_ok ? p.ws + ((b == 0) ? p.w.off_dfeat : p.w.off_dh[8 - b]) + (size_t)tile_ws * 4 * kBlobBytes : nullptr;
+        uint8_t* gdst = tile_ok ? p.ws + p.w.off_dh[7 - b] + (size_t)tile_ws * 4 * kBlobBytes : nullptr;
         // rolled on purpose: one 32-column body stays resident in the instruction cache (see nb_mlp_tc.cu)
 #pragma unroll 1
         for (int c32 = half * 4; c32 < half * 4 + 4; ++c32) {
           float v[32];
           tmem_ld32(t_addr + (uint32_t)c32 * 32u, v);
           tmem_ld_wait();
-          if (b == 1) {   // density head: d h7 += d sigma * W_sigma   (NeRF.py:43)
+          if (b == 0) {   // density head: d h7 += d sigma * W_sigma   (NeRF.py:43)
             const float* w = c_bw.ws + c32 * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaf(dr.w, w[j], v[j]);
@@ -298,6 +296,7 @@ struct WgradJob {
   const uint8_t* b2;
   int b2_blobs, b2_first, n2_blk, n2_valid;
   float* out2;
+  int ld2;               // row stride of out2
   // optional rank-1 rider on the B operand (density head on the last trunk activation): sig_out[k] += sum_p d_raw[p][3] * B[p][k]
   // and sig_bias += sum_p d_raw[p][3], on the CUDA cores of the bias warps, so that B is not streamed a second time
   const float* sig_draw;
@@ -564,7 +563,7 @@ mlp_wgrad_kernel(const WgradParams p) {
         tmem_ld32(tmem_base + ((q * 32u) << 16) + 256u + (uint32_t)c32 * 32u, v);
         tmem_ld_wait();
         if (m >= J.m_first && m < J.m_valid) {
-          float* dst = J.out2 + (size_t)(m - J.m_first) * J.ld + c32 * 32;
+          float* dst = J.out2 + (size_t)(m - J.m_first) * J.ld2 + c32 * 32;
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj)
             if (c32 * 32 + jj < J.n2_valid) atomicAdd(dst + jj, v[jj]);
@@ -581,23 +580,60 @@ mlp_wgrad_kernel(const WgradParams p) {
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------
+// (3) gradients of the folded layers from G = dg^T h7 [128][256] and s = column sums of dg [128]  (fp32, 25 MFLOP)
+//     feat = Wf h7 + bf,  pre_g = Wd_a feat + Wd_b PE(d) + bd   (Wd_a = Wd[:, :256])
+//       dWf   = Wd_a^T G              dWd_a = G Wf^T + s (x) bf            dbf = Wd_a^T s            dbd = s
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fold_grads_kernel(const float* __restrict__ prm, NbParamLayout L, const float* __restrict__ fold_g, float* __restrict__ grad) {
+  const float* G = fold_g;
+  const float* sdg = fold_g + 128 * 256;
+  const int t = threadIdx.x;
+  __shared__ float sh[256];
+  if (blockIdx.x < 256) {                      // dWf[j][:] += sum_n Wd_a[n][j] G[n][:]  ;  dbf[j] += sum_n Wd_a[n][j] s[n]
+    const int j = blockIdx.x;
+    if (t < 128) sh[t] = prm[L.wd + (size_t)t * 283 + j];
+    __syncthreads();
+    float acc = 0.f;
+#pragma unroll 8
+    for (int n = 0; n < 128; ++n) acc = fmaf(sh[n], G[(size_t)n * 256 + t], acc);
+    grad[L.wf + (size_t)j * 256 + t] += acc;
+    if (t == 0) {
+      float b = 0.f;
+      for (int n = 0; n < 128; ++n) b = fmaf(sh[n], sdg[n], b);
+      grad[L.bf + j] += b;
+    }
+  } else if (blockIdx.x < 256 + 128) {         // dWd_a[n][j] += sum_k G[n][k] Wf[j][k] + s[n] bf[j]
+    const int n = blockIdx.x - 256;
+    sh[t] = G[(size_t)n * 256 + t];
+    __syncthreads();
+    const float* wf = prm + L.wf + (size_t)t * 256;      // row j = t of Wf
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 256; ++k) acc = fmaf(sh[k], wf[k], acc);
+    grad[L.wd + (size_t)n * 283 + t] += acc + sdg[n] * prm[L.bf + t];
+  } else {                                     // dbd += s
+    if (t < 128) grad[L.bd + t] += sdg[t];
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 size_t nb_tc_bwd_packed_bytes() { return bwd_w_off(kBwdSteps); }
-size_t nb_tc_bwd_ws_bytes(const nb_mlp_desc&, long long P) { return bwd_ws_layout(P).total + 256; }
+size_t nb_tc_bwd_ws_bytes(const nb_mlp_desc&, long long P) { return bwd_ws_layout(P).total + kFoldFloats * sizeof(float) + 256; }
 
-void nb_tc_bwd_add_blobs(const NbParamLayout& L, const std::function<void(size_t, int, int, int, int, int, int, int)>& add) {
+void nb_tc_bwd_add_blobs(const NbParamLayout& L, const std::function<void(size_t, int, int, int, int, int, int, int, int)>& add) {
   // blob[n][k] = W[k0+k][n0+n]  (B = W^T, rows = in-features, K = out-features)
-  for (int kb = 0; kb < 2; ++kb) add(L.wd, 283, 1, 0, 64 * kb, 256, 256, 128);              // step 0: Wd[:, :256]
-  for (int kb = 0; kb < 4; ++kb) add(L.wf, 256, 1, 0, 64 * kb, 256, 256, 256);              // step 1: Wf
-  const int layers[7] = {7, 6, 5, 4, 3, 2, 1};                                              // steps 2..8
+  for (int kb = 0; kb < 2; ++kb) add(0, 256, 1, 0, 64 * kb, 256, 256, 128, 1);              // step 0: the folded W' = Wd[:, :256] . Wf  (128 x 256)
+  const int layers[7] = {7, 6, 5, 4, 3, 2, 1};                                              // steps 1..7
   for (int i = 0; i < 7; ++i) {
     const int l = layers[i];
     const size_t src = L.w[l] + (l == 5 ? 63 : 0);                                           // skip layer: the h columns of W5
-    for (int kb = 0; kb < 4; ++kb) add(src, L.in_dim[l], 1, 0, 64 * kb, 256, 256, 256);
+    for (int kb = 0; kb < 4; ++kb) add(src, L.in_dim[l], 1, 0, 64 * kb, 256, 256, 256, 0);
   }
 }
 
@@ -606,8 +642,8 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
                    cudaStream_t st, int stages) {
   const NbParamLayout L = nb_param_layout(*d);
   const BwdWs W = bwd_ws_layout(P);
-  if (!ws || ws_bytes < W.total) {
-    NB_SET_ERR(h, "mlp bf16 backward: workspace %zu < %zu bytes", ws_bytes, W.total);
+  if (!ws || ws_bytes < W.total + kFoldFloats * sizeof(float)) {
+    NB_SET_ERR(h, "mlp bf16 backward: workspace %zu < %zu bytes", ws_bytes, W.total + kFoldFloats * sizeof(float));
     return NB_ERR_WORKSPACE;
   }
   NB_REQUIRE(h, ((uintptr_t)d_raw & 15) == 0 && ((uintptr_t)ws & 15) == 0 && ((uintptr_t)act_save & 15) == 0,
@@ -686,14 +722,15 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
         add(dh[l], 4, 0, 4, stash + S.off_h[l - 1], 4, 0, 4, grad + L.w[l], 256, 0, 256, 256, grad + L.b[l]);
       }
     }
-    // feature layer, view layer, heads
-    // feature layer; the density head (dW_sigma = d_sigma^T h8, db_sigma) rides on its B operand instead of streaming h8 again
-    add(w8 + W.off_dfeat, 4, 0, 4, stash + S.off_h[7], 4, 0, 4, grad + L.wf, 256, 0, 256, 256, grad + L.bf);
-    wp.job[nj - 1].sig_draw = d_raw; wp.job[nj - 1].sig_out = grad + L.ws; wp.job[nj - 1].sig_bias = grad + L.bs;
-    // view layer: one job, dg read once against both input blocks [features (256) | PE(viewdir) (27)]
-    add(w8 + W.off_dg, 2, 0, 2, stash + S.off_feat, 4, 0, 4, grad + L.wd, 283, 0, 128, 256, grad + L.bd);
+    // folded feature + view layers: ONE job G = dg^T [h7 | PE(viewdir)].  Its h7 block (128 x 256, into the fold scratch) carries the
+    // gradients of Wf, b_feat and Wd[:, :256] (fold_grads_kernel below); its PE block is dWd[:, 256:283] directly.  The density head
+    // (dW_sigma = d_sigma^T h7, db_sigma) rides on the h7 operand.  dg is read once, h7 once: 7 blobs where the unfolded layers took 15.
+    float* fold_g = reinterpret_cast<float*>((uint8_t*)ws + W.total);              // [128][256] G  +  [128] column sums of dg
+    NB_CUDA(h, cudaMemsetAsync(fold_g, 0, kFoldFloats * sizeof(float), st));
+    add(w8 + W.off_dg, 2, 0, 2, stash + S.off_h[7], 4, 0, 4, fold_g, 256, 0, 128, 256, fold_g + 128 * 256);
     { WgradJob& j = wp.job[nj - 1]; j.b2 = stash + S.off_embd; j.b2_blobs = 1; j.b2_first = 0; j.n2_blk = 1; j.n2_valid = 27;
-      j.out2 = grad + L.wd + 256; weight[nj - 1] += 1; }
+      j.out2 = grad + L.wd + 256; j.ld2 = 283; weight[nj - 1] += 1;
+      j.sig_draw = d_raw; j.sig_out = grad + L.ws; j.sig_bias = grad + L.bs; }
     // rgb head: A = d_raw blob (cols 0..2 = d_rgb), stored twice so that M = 128 is addressable
     add(w8 + W.off_draw, 2, 0, 2, stash + S.off_g, 2, 0, 2, grad + L.wc, 128, 0, 3, 128, grad + L.bc);          // dWc, dbc
     wp.n_jobs = nj;
@@ -705,6 +742,8 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
     int begin = h->sm_count;
     if ((long long)begin > n_tiles * 2) begin = (int)(n_tiles * 2);
     mlp_wgrad_kernel<<<begin, kWgThreads, kWgSmemBytes, st>>>(wp);
+    NB_LAUNCHED(h);
+    fold_grads_kernel<<<256 + 128 + 1, 256, 0, st>>>(params, L, fold_g, grad);
     NB_LAUNCHED(h);
   }
   return NB_OK;

@@ -672,7 +672,7 @@ def test_cuda_graph_train_step_equals_eager():
         assert torch.allclose(loss, l_e, rtol=1e-5, atol=1e-7), (i, loss, l_e)
         for got, ref in ((net_g.model_coarse.flat_grad, gc_e), (net_g.model_fine.flat_grad, gf_e)):
             assert float((got - ref).norm() / ref.norm()) <= (1e-5 if i == 0 else 1e-2), i      # later steps: Adam's sign-like first updates amplify atomics-order noise
-        assert eng.launch_count() - before <= 4       # host-side launches per step: 2 re-packs + 2 Adam (the rest is ONE graph launch)
+        assert eng.launch_count() - before <= 6       # host-side launches per step: 2 x (fold + re-pack) + 2 Adam (the rest is ONE graph launch)
     assert int(gs.ctr) == 3 * gs._per_step
 
 
