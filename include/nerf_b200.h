@@ -230,6 +230,10 @@ typedef struct nb_render_cfg {
   uint64_t seed, offset_c, offset_f;
   int64_t cdf_rows;   /* nb_sample_pdf's cdf_rows (summation order of the fine pdf/cdf) */
   const uint64_t* ctr; /* optional device-resident Philox counter added to offset_c / offset_f (nb_counter_add) */
+  int32_t exact_last;  /* NB_BF16 only: re-evaluate the LAST sample of every ray on the fp32 path before compositing.  That sample's
+                        * interval is 1e10 (nerf_process.py:98), so its alpha is a step function of sign(sigma): with the flag the
+                        * decision is the fp32 path's (costs one fp32 MLP pass over N points per network; default 0) */
+  int32_t reserved;
 } nb_render_cfg;
 /* Bytes of caller workspace the drivers need for N rays (train != 0: including the activation stash). */
 int nb_render_workspace_bytes(nb_handle_t h, const nb_mlp_desc* d, int64_t N, const nb_render_cfg* cfg, int32_t train,

@@ -27,7 +27,7 @@ class MlpDesc(C.Structure):
 
 class RenderCfg(C.Structure):
     _fields_ = [('S_c', C.c_int32), ('S_f', C.c_int32), ('precision', C.c_int32), ('u_mode', C.c_int32),
-                ('seed', C.c_uint64), ('offset_c', C.c_uint64), ('offset_f', C.c_uint64), ('cdf_rows', C.c_int64), ('ctr', C.c_void_p)]
+                ('seed', C.c_uint64), ('offset_c', C.c_uint64), ('offset_f', C.c_uint64), ('cdf_rows', C.c_int64), ('ctr', C.c_void_p), ('exact_last', C.c_int32), ('reserved', C.c_int32)]
 
 
 _p = C.c_void_p

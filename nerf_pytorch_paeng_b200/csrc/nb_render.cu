@@ -17,9 +17,23 @@ struct Carve {
 
 struct Plan {
   float *z_c, *w_c, *z_f, *w_f, *raw, *d_raw, *d_rgb, *rays_d, *rgb_tmp, *disp_tmp;
-  uint8_t *act, *mlp_ws;
-  size_t act_bytes, mlp_ws_bytes, total;
+  float *z_last, *raw_last;        // exact_last: depth and fp32 network output of every ray's last sample
+  uint8_t *act, *mlp_ws, *fp32_ws;
+  size_t act_bytes, mlp_ws_bytes, fp32_ws_bytes, total;
 };
+
+// exact_last (nb_render_cfg): the reference gives the LAST sample of a ray a 1e10-long interval (nerf_process.py:98), so its alpha is
+// a step function of sign(sigma_last) and the bf16 path's ~1e-3 noise on sigma can land a ray on the other side of the step when
+// |sigma_last| is tiny (random-init networks).  With the flag set the last sample of every ray is re-evaluated on the fp32 path
+// (N points per network) and its network output replaces the bf16 one before compositing.
+__global__ void gather_last_kernel(long long N, int S, const float* __restrict__ z, float* __restrict__ z_last) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) z_last[i] = z[i * S + S - 1];
+}
+__global__ void scatter_last_kernel(long long N, int S, const float4* __restrict__ raw_last, float4* __restrict__ raw) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) raw[i * S + S - 1] = raw_last[i];
+}
 
 int make_plan(nb_handle_t h, const nb_mlp_desc* d, int64_t N, const nb_render_cfg* c, int train, void* ws, Plan* p) {
   const int64_t S = c->S_c + (c->S_f > 0 ? c->S_f : 0);
@@ -44,6 +58,13 @@ int make_plan(nb_handle_t h, const nb_mlp_desc* d, int64_t N, const nb_render_cf
   p->mlp_ws_bytes = wf > wb ? wf : wb;
   p->act = cv.take<uint8_t>(act);
   p->mlp_ws = cv.take<uint8_t>(p->mlp_ws_bytes);
+  p->z_last = p->raw_last = nullptr; p->fp32_ws = nullptr; p->fp32_ws_bytes = 0;
+  if (c->exact_last && c->precision == NB_BF16) {
+    if ((rc = nb_mlp_workspace_bytes(h, d, N, NB_FP32, 0, &p->fp32_ws_bytes))) return rc;
+    p->z_last = cv.take<float>(N);
+    p->raw_last = cv.take<float>(N * 4);
+    p->fp32_ws = cv.take<uint8_t>(p->fp32_ws_bytes);
+  }
   p->total = cv.off + 1024;
   return NB_OK;
 }
@@ -71,6 +92,15 @@ int run_net(nb_handle_t h, const nb_mlp_desc* d, const nb_render_cfg* c, const P
   if (rc) return rc;
   if ((rc = nb_mlp_forward_rays(h, d, params, packed, N, S, rays, z, p.raw, train ? p.act : nullptr, c->precision, p.mlp_ws,
                                 p.mlp_ws_bytes, st))) return rc;
+  if (p.z_last != nullptr && N > 0) {      // exact last-sample decision: fp32 re-evaluation of z[:, S-1] (see gather_last_kernel)
+    const int blocks = nb_cdiv(N, 256);
+    gather_last_kernel<<<blocks, 256, 0, st>>>((long long)N, S, z, p.z_last);
+    NB_LAUNCHED(h);
+    if ((rc = nb_mlp_forward_rays(h, d, params, nullptr, N, 1, rays, p.z_last, p.raw_last, nullptr, NB_FP32, p.fp32_ws, p.fp32_ws_bytes, st)))
+      return rc;
+    scatter_last_kernel<<<blocks, 256, 0, st>>>((long long)N, S, reinterpret_cast<const float4*>(p.raw_last), reinterpret_cast<float4*>(p.raw));
+    NB_LAUNCHED(h);
+  }
   float* rgb = rgb_out ? rgb_out : p.rgb_tmp;
   // the fine pass of render_rays drops weights/depth/acc (nerf_process.py:211-216); the coarse weights feed sample_pdf
   if ((rc = nb_composite_forward(h, N, S, p.raw, z, p.rays_d, rgb, disp_out ? disp_out : p.disp_tmp, nullptr, fine ? nullptr : w,

@@ -270,13 +270,13 @@ class Engine:
     def _u_mode(u):
         return 2 if u is None else (0 if u.dim() == 1 else 1)
 
-    def render_rays(self, desc, nets, rays, lower, span, n_fine, precision, t_rand=None, u=None, seed=0, offset_c=0, offset_f=0, cdf_rows=0, ctr=None):
+    def render_rays(self, desc, nets, rays, lower, span, n_fine, precision, t_rand=None, u=None, seed=0, offset_c=0, offset_f=0, cdf_rows=0, ctr=None, exact_last=False):
         """nerf_process.py:185-216 as one nb_render_rays call.  nets = ((flat_c, packed_c), (flat_f, packed_f)).
         Returns (rgb_c, disp_c, rgb_f, disp_f); the fine pair is None when n_fine == 0."""
         rays = _chk32(rays, 'rays')
         n = rays.shape[0]
         cfg = RenderCfg(lower.numel(), max(int(n_fine), 0), precision, self._u_mode(u), seed, offset_c, offset_f, int(cdf_rows),
-                        None if ctr is None else ctr.data_ptr())
+                        None if ctr is None else ctr.data_ptr(), 1 if exact_last else 0, 0)
         ws = self._fused_ws(desc, n, cfg, False)
         (pc, kc), (pf, kf) = nets
         rgb_c, disp_c = self.empty(n, 3), self.empty(n)
@@ -287,14 +287,14 @@ class Engine:
         return rgb_c, disp_c, rgb_f, disp_f
 
     def train_rays(self, desc, nets, grads, rays, target, n_global, lower, span, n_fine, precision, loss_buf, out, which=3,
-                   t_rand=None, u=None, seed=0, offset_c=0, offset_f=0, accumulate=False, target_ready=None, cdf_rows=0, ctr=None):
+                   t_rand=None, u=None, seed=0, offset_c=0, offset_f=0, accumulate=False, target_ready=None, cdf_rows=0, ctr=None, exact_last=False):
         """train.py:53-69 minus the optimizer as nb_train_rays.  `out` is a dict that receives / supplies the
         rgb_c, disp_c, rgb_f, disp_f tensors (so a coarse call and a fine call can share it); which = nets bit mask."""
         rays = _chk32(rays, 'rays')
         target = _chk32(target, 'target')
         n = rays.shape[0]
         cfg = RenderCfg(lower.numel(), max(int(n_fine), 0), precision, self._u_mode(u), seed, offset_c, offset_f, int(cdf_rows),
-                        None if ctr is None else ctr.data_ptr())
+                        None if ctr is None else ctr.data_ptr(), 1 if exact_last else 0, 0)
         ws = self._fused_ws(desc, n, cfg, True)
         (pc, kc), (pf, kf) = nets
         for tag, bit in (('c', 1), ('f', 2)):

@@ -135,7 +135,7 @@ def _fused_sampling_args(n, opts, device):
             u = _injected(opts, 'u')
         off_f = _next_offset(n * n_fine // 4 + 1)
     return dict(lower=lower, span=span, n_fine=n_fine, t_rand=_injected(opts, 't_rand'), u=u, seed=_seed(opts),
-                offset_c=off_c, offset_f=off_f, cdf_rows=_cdf_rows(opts, n))
+                offset_c=off_c, offset_f=off_f, cdf_rows=_cdf_rows(opts, n), exact_last=bool(getattr(opts, 'exact_last_sample', False)))
 
 
 def pre_process(rays, posenc, opts, z_vals=None, weights=None, isFine=False):

@@ -505,7 +505,7 @@ def test_fused_driver_rejects_small_workspace():
     dev = torch.device('cuda', 0)
     eng = get_engine(dev)
     m = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).to(dev).model_coarse
-    cfg = RenderCfg(64, 128, NB_BF16, 2, 0, 0, 0, 0, None)
+    cfg = RenderCfg(64, 128, NB_BF16, 2, 0, 0, 0, 0, None, 0, 0)
     need = C.c_size_t()
     eng._call('nb_render_workspace_bytes', C.byref(m.desc), 256, C.byref(cfg), 0, C.byref(need))
     assert need.value > 256 * 192 * 16
@@ -579,7 +579,7 @@ def test_fused_driver_workspace_is_not_overrun():
     tgt = torch.rand(n, 3, device=dev)
     opts = make_opts()
     lower, span = NP._coarse_bins(opts, dev)
-    cfg = RenderCfg(64, 128, NB_BF16, 2, 9, 0, 100000, 0, None)
+    cfg = RenderCfg(64, 128, NB_BF16, 2, 9, 0, 100000, 0, None, 0, 0)
     need = C.c_size_t()
     eng._call('nb_render_workspace_bytes', C.byref(nc.desc), n, C.byref(cfg), 1, C.byref(need))
     G = 4096

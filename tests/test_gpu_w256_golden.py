@@ -149,3 +149,32 @@ def test_fused_train_grads_vs_reference_w256(eng, tag, precision):
     tol_g, tol_l = (1e-2, 2e-3) if precision == 'bf16' else (1e-3, 1e-5)
     assert abs(rep['loss_c'] - rep['ref_loss_c']) <= tol_l and abs(rep['loss_f'] - rep['ref_loss_f']) <= tol_l, rep
     assert rep['grad_rel_err_coarse'] <= tol_g and rep['grad_rel_err_fine'] <= tol_g, rep
+
+
+@pytest.mark.parametrize('tag', ['plain', 'dens30'])
+def test_fused_render_exact_last_sample_w256(eng, tag):
+    """opts.exact_last_sample (nb_render_cfg.exact_last): the last sample of every ray is re-evaluated on the fp32 path, so the
+    1e10-interval step decision (nerf_process.py:98) is the fp32 path's: the bf16 fused render then meets the >= 50 dB bar over
+    ALL rays of the plain random-init fixture, no exclusions."""
+    from nerf_pytorch_paeng_b200 import trainer
+    g = load_golden(f'render_train_w256_{tag}.npz')
+    net = build_net(g, 'bf16')
+    opts = make_opts(g)
+    opts.exact_last_sample = True
+    rays = cu(np.concatenate([g['rays_o'], g['rays_d']], -1))
+    with torch.no_grad():
+        out = trainer.render_rays_fused(net, rays, opts)
+    rep = {'tag': tag, 'mode': 'bf16 + exact_last_sample'}
+    for k in ('c', 'f'):
+        got, ref = out['rgb_' + k].cpu().numpy(), g['rgb_' + k]
+        rep[f'psnr_{k}_all_dB'] = psnr(got, ref)
+        rep[f'max_abs_{k}'] = float(np.abs(got - ref).max())
+    print('\n' + json.dumps(rep))
+    record('fused_render_exact_last_sample_w256', rep)
+    assert rep['psnr_c_all_dB'] >= 50.0 and rep['psnr_f_all_dB'] >= 50.0, rep
+    # the same option through the training driver: losses of one nb_train_rays call against the reference's
+    for m in (net.model_coarse, net.model_fine):
+        m.bind_flat_grad().zero_()
+    o2 = trainer.render_losses_and_grads(net, rays, cu(g['target']), opts)
+    loss = o2['loss_buf'].cpu().numpy()
+    assert abs(float(loss[0]) - float(g['loss_c'])) <= 2e-4 and abs(float(loss[1]) - float(g['loss_f'])) <= 2e-4, (loss, float(g['loss_c']), float(g['loss_f']))
