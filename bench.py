@@ -368,8 +368,8 @@ def run_ours(args):
     tsrc = traffic.get('source', 'profiles/traffic.json (ncu --set full dram__bytes of an earlier run of this command; not measured in this run)')
     flop_step = FLOP_PER_POINT_TRAIN * N_RAYS * POINTS_PER_RAY
     fwd_tf = FLOP_PER_POINT_FWD * pts_per_launch / (avg['fwd'] / 1e3) / 1e12
-    # wgrad's algorithmic HBM bytes: every 16 KB operand blob its 12 jobs read: 85 blobs per 128-point tile
-    WGRAD_BYTES_PER_POINT = 85 * 16384 / 128.0
+    # wgrad's algorithmic HBM bytes: every 16 KB operand blob its 11 jobs read: 78 blobs per 128-point tile
+    WGRAD_BYTES_PER_POINT = 78 * 16384 / 128.0
     other = {'mlp_fwd_chain_kernel<train>': {'bound': 'tensor', 'achieved': fwd_tf, 'unit': 'TFLOP/s', 'frac': fwd_tf / peak_tf,
                                              'avg_launch_ms': avg['fwd'], 'traffic': traffic.get('mlp_fwd_chain_kernel_bytes_per_launch')}}
     if args.precision == 'bf16':
@@ -381,7 +381,7 @@ def run_ours(args):
         other['mlp_wgrad_kernel as an HBM stream'] = {
             'bound': 'hbm', 'achieved': wg_gbs, 'peak': peak_hbm, 'unit': 'GB/s', 'frac': wg_gbs / peak_hbm,
             'algorithmic_bytes_per_launch': WGRAD_BYTES_PER_POINT * pts_per_launch,
-            'note': 'the kernel streams 10.9 KB/point of stashed operands; this is the roofline that binds it in practice (DESIGN.md section 4)'}
+            'note': 'the kernel streams 9.98 KB/point of stashed operands; this is the roofline that binds it in practice (DESIGN.md section 4)'}
         # headline: the dominant kernel by time share (profiles/*launches*.csv) against SURVEY 8(d)'s bound for K4, the tensor pipe
         roofline = {'bound': 'tensor', 'achieved': wg_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': wg_tf / peak_tf,
                     'traffic': traffic.get('mlp_wgrad_kernel_bytes_per_launch'), 'traffic_source': tsrc,
