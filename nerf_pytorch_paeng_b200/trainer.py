@@ -243,7 +243,7 @@ def train_step(model, optimizer, rays, target, opts, dist_ctx=None):
     Data parallel (dist_ctx): every rank normalises by the global ray count, the two flat gradient buffers and the two
     losses live in one joint buffer and are summed by a single all-reduce.  NB_DP_MODE=overlap restores the earlier
     schedule (coarse all-reduce launched before the fine pass, three collectives per step) for comparison.  Default ('auto'): the
-    copy-engine exchange of distributed.PeerGradExchange ('peer'), else 'joint'."""
+    copy-engine exchange of distributed.PeerGradExchange ('peer') for world sizes up to NB_DP_PEER_MAX_WORLD (2), else 'joint'."""
     n_global = rays.shape[0] * (dist_ctx.world_size if dist_ctx is not None else 1)
     if dist_ctx is None:
         out = render_losses_and_grads(model, rays, target, opts, n_global=n_global)
@@ -252,7 +252,10 @@ def train_step(model, optimizer, rays, target, opts, dist_ctx=None):
     mode = os.environ.get('NB_DP_MODE', 'auto')
     if mode == 'auto':        # copy-engine exchange when the optimizer can fold the sum (FlatAdam) and symmetric memory is available
         mode = 'joint'
-        if isinstance(optimizer, FlatAdam) and rays.is_cuda and getattr(dist_ctx, '_peer_ok', True):
+        # measured (profiles/r02_scaling_*): at 2 GPUs the peer exchange wins (5.61 vs 5.69 ms/step); at 8 GPUs its 7 pushes per part
+        # cost more than they hide (4.98 vs 4.92 ms/step with one NCCL all-reduce), so larger worlds keep the all-reduce
+        if (isinstance(optimizer, FlatAdam) and rays.is_cuda and getattr(dist_ctx, '_peer_ok', True)
+                and dist_ctx.world_size <= int(os.environ.get('NB_DP_PEER_MAX_WORLD', '2'))):
             try:
                 if getattr(dist_ctx, '_peer_exchange', None) is None:
                     from .distributed import PeerGradExchange
