@@ -160,7 +160,10 @@ int nb_mlp_act_bytes(nb_handle_t h, const nb_mlp_desc* d, int64_t P, int32_t pre
 int nb_mlp_workspace_bytes(nb_handle_t h, const nb_mlp_desc* d, int64_t P, int32_t precision, int32_t backward,
                            size_t* out);
 /* Bytes of the packed (tile-layout bf16) copy of one net's weights and the packer itself
- * (call after load_state_dict / every optimizer step).  NB_BF16 only. */
+ * (call after load_state_dict / every optimizer step).  NB_BF16 only.  The packer also folds the activation-free feature layer
+ * into the view layer (model/NeRF.py:44,47-49: W' = Wd[:, :W] . Wf, b' = Wd[:, :W] . b_feat + b_d, in fp32), which the bf16
+ * forward / backward kernels use instead of two separate GEMMs; the gradients of linear_feat and linear_d are recovered exactly
+ * (up to fp32 rounding) by nb_mlp_backward. */
 int nb_mlp_packed_bytes(nb_handle_t h, const nb_mlp_desc* d, size_t* out);
 int nb_mlp_pack(nb_handle_t h, const nb_mlp_desc* d, const float* params, void* packed, void* stream);
 /* model/NeRF.py:33-52 on a materialised embedding x[P, ld_x] (first in_x+in_d columns used):

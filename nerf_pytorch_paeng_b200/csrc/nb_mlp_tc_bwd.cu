@@ -11,9 +11,10 @@
 //  (2) wgrad -- dW_l = dY_l^T . X_l reduced over all points.  The stashed blobs ([128 points x 64 features] in the chunk-major
 //      layout of stash_off(): [point/64][feature/8][point%64][8 features]) are exactly SWIZZLE_NONE "MN-major" UMMA operands, so
 //      both A = dY_l and B = X_l are bulk-loaded (8 KB half blobs) and fed to tcgen05.mma without any transposition; the 256x256 fp32 accumulator of one weight matrix fills the
-//      512 TMEM columns.  The 12 (layer, input-block) jobs form one line of work cut into equal-traffic slices, one per
-//      CTA (wgrad is HBM-bound: 85 operand blobs per tile, see wg_segment); the view layer's two input blocks share one
-//      job (second accumulator region) and the density head rides on the feature job's B operand; bias gradients are
+//      512 TMEM columns.  The 11 (layer, input-block) jobs form one line of work cut into equal-traffic slices, one per
+//      CTA (wgrad is HBM-bound: 78 operand blobs per tile, see wg_segment); the folded feature + view layers are ONE job
+//      G = dg^T [h7 | PE(d)] (second accumulator region for the PE block; fold_grads_kernel maps G to dWf, dbf and dWd[:, :256])
+//      and the density head rides on that job's h7 operand; bias gradients are
 //      column sums of the dY tiles taken from shared memory by spare warps; results are added to the flat fp32
 //      gradient with red.global.add (v4 where the rows are 16-byte aligned).
 #include <stdlib.h>
