@@ -395,3 +395,46 @@ def test_tc_buffers_are_not_overrun(setup):
     eng.mlp_backward(m.desc, flat, pk, NB_BF16, P, act2, d_raw, ref)
     torch.cuda.synchronize()
     assert float((got - ref).norm() / ref.norm()) <= 1e-4
+
+
+@pytest.mark.parametrize('n,s', [(5, 60), (333, 192)])
+def test_tc_buffers_guard_bands(setup, n, s):
+    """No out-of-bounds writes: the packed-weight buffer, the activation stash and the backward workspace are placed between
+    sentinel-filled guard bands (1 MiB each side) and exactly as large as the size queries say; the bands must survive pack,
+    forward (train), dgrad, wgrad and the fold kernels untouched.  (compute-sanitizer is not available on the GPU pool.)"""
+    import ctypes as C
+    from nerf_pytorch_paeng_b200._lib import NB_BF16
+    eng, net, g = setup
+    m = net.model_fine
+    m.precision = NB_BF16
+    flat = m.flat_params()
+    rays, z = make_rays(g, n, s, seed=4)
+    rays_t, z_t = cu(rays), cu(z)
+    P = n * s
+    G = 1 << 20
+    act_b, ws_f, ws_b = eng.mlp_bytes(m.desc, P, NB_BF16)
+    pk_b = eng.mlp_packed_bytes(m.desc)
+
+    def guarded(nbytes):
+        nbytes = (nbytes + 255) // 256 * 256
+        t = torch.full((nbytes + 2 * G,), 0xAB, dtype=torch.uint8, device='cuda')
+        return t, t[G:G + nbytes]
+    pk_full, pk = guarded(pk_b)
+    act_full, act = guarded(act_b)
+    ws_full, ws = guarded(max(ws_f, ws_b))
+    raw = torch.empty(P, 4, device='cuda')
+    d_raw = torch.randn(P, 4, device='cuda') * 1e-2
+    grad = torch.zeros_like(flat)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    eng._call('nb_mlp_pack', C.byref(m.desc), ptr(flat), ptr(pk), eng.stream)
+    eng._call('nb_mlp_forward_rays', C.byref(m.desc), ptr(flat), ptr(pk), n, s, ptr(rays_t), ptr(z_t), ptr(raw), ptr(act), NB_BF16,
+              ptr(ws), ws.numel(), eng.stream)
+    eng._call('nb_mlp_backward', C.byref(m.desc), ptr(flat), ptr(pk), P, ptr(act), ptr(d_raw), ptr(grad), 0, NB_BF16, ptr(ws), ws.numel(),
+              eng.stream)
+    torch.cuda.synchronize()
+    for name, full, inner in (('packed', pk_full, pk), ('stash', act_full, act), ('workspace', ws_full, ws)):
+        assert bool((full[:G] == 0xAB).all()) and bool((full[G + inner.numel():] == 0xAB).all()), f'{name}: guard band overwritten'
+    assert torch.isfinite(raw).all() and torch.isfinite(grad).all()
+    # and the guarded run computes what the ordinary route computes
+    raw2, act2 = eng.mlp_forward(m.desc, flat, m.packed_weights(), NB_BF16, rays=rays_t, z=z_t, save=True)
+    assert torch.equal(raw, raw2)
