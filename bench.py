@@ -546,7 +546,10 @@ def run_ours(args):
             'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD_LLFF if llff else WORKLOAD, 'rays_per_gpu': N_RAYS, 'global_rays': N_RAYS * world, 'samples': [S_C, S_F],
-                       'precision': args.precision, 'parallelism': f'ray-sharded data parallel x{world}, one NCCL all-reduce of 1,191,690 fp32 (gradients of both nets + the two losses)',
+                       'precision': args.precision, 'parallelism': f'ray-sharded data parallel x{world}, ' + (
+                           'gradients exchanged by copy-engine pushes into peer symmetric memory, sum folded into Adam (PeerGradExchange)'
+                           if (dctx is not None and getattr(dctx, '_peer_exchange', None) is not None and graphed is None)
+                           else 'one NCCL all-reduce of 1,191,690 fp32 (gradients of both nets + the two losses)') if world > 1 else 'single GPU',
                        'l2': 'per-step working set (activation stash >= 5 GB) exceeds the 126 MB L2; ring of 8 distinct ray batches',
                        'timed_region': f'{args.steps} steps = {ms_step * args.steps:.0f} ms; a sustained figure over 12,000 steps of the same step is in profiles/ (train_demo)',
                        'loss': float(loss.sum())},
