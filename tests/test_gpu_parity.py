@@ -495,3 +495,42 @@ def test_sample_pdf_torch_cuda_order_fixture(eng, rows):
     # and against the oracle's restatement of the same order
     o_zf, o_zs, o_inds = orc.fine_z(g[f'n{rows}_z'], g[f'n{rows}_w'], npy(u), order='cuda', rows=rows)
     assert np.array_equal(npy(inds), o_inds) and np.array_equal(npy(z_f), o_zf)
+
+
+def test_fp32_render_frame_default_chunk_large_frame(eng):
+    """test()/render() on the fp32 path with the DEFAULT chunk on a frame of >= 65536 pixels.  A pass of
+    65536 rays x 192 samples is 12.6 M points: more than the 65535 x 128 rows the SGEMM's grid.y covers in one launch (now issued
+    as row slabs) and ~30 GB of fp32 workspace (now capped at 4 M points per pass by render_frame).  Also drives a single 9 M-point
+    fp32 MLP call directly to cross the grid.y limit."""
+    from nerf_pytorch_paeng_b200 import trainer
+    from nerf_pytorch_paeng_b200.model import NeRF
+    g = load_golden('raygen.npz')
+    torch.manual_seed(0)
+    net = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).cuda().set_precision('fp32')
+    H = W = 400
+    K = np.array([[555.5, 0, W / 2], [0, 555.5, H / 2], [0, 0, 1.]])
+    pose = cu(g['pose'])
+    opts = make_opts(seed=3)
+    rgb, disp = trainer.render_frame(net, H, W, K, pose, opts)            # default chunk
+    torch.cuda.synchronize()
+    assert rgb.shape == (H * W, 3) and bool(torch.isfinite(rgb).all()) and bool(torch.isfinite(disp).all())
+    # the same frame on the bf16 path with the chunking the fp32 cap produced (=> the same Philox counters per chunk): the two
+    # precisions must agree up to bf16 noise
+    from nerf_pytorch_paeng_b200 import nerf_process
+    cap = (4 << 20) // 192
+    nerf_process._counter[0] = 0
+    rgb_a, _ = trainer.render_frame(net, H, W, K, pose, opts, chunk=cap)
+    net.set_precision('bf16')
+    nerf_process._counter[0] = 0
+    rgb_b, _ = trainer.render_frame(net, H, W, K, pose, opts, chunk=cap)
+    err = (rgb_a - rgb_b).abs().max(-1)[0]
+    assert float(err.median()) <= 5e-3, float(err.median())
+    # one fp32 MLP call above grid.y * 128 rows
+    net.set_precision('fp32')
+    m = net.model_fine
+    n_pts = 65535 * 128 + 4096
+    x = torch.zeros(n_pts, 90, device='cuda')
+    x[:, 0] = 1.0
+    raw, _ = eng.mlp_forward(m.desc, m.flat_params(), None, m.precision, x=x)
+    torch.cuda.synchronize()
+    assert bool(torch.equal(raw[0], raw[-1])) and bool(torch.isfinite(raw[-1]).all())     # identical rows in -> identical rows out, incl. the last slab
