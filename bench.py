@@ -500,6 +500,27 @@ def run_ours(args):
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
         sms = float(tt) / args.steps
         strong = {'scaling': 'strong', 'global_rays': N_RAYS, 'rays_per_gpu': n_loc, 'ms_per_step': sms, 'value': N_RAYS / (sms / 1e3), 'unit': 'rays/s'}
+        # at ~1 ms per step the host's 22 launches matter: the same step as ONE captured CUDA graph (render + loss + backward +
+        # the NCCL all-reduce of the joint buffer), Adam and the re-pack following from the host
+        if args.precision == 'bf16':
+            try:
+                gs = trainer.GraphedTrainStep(model, opts, n_loc, dev, dist_ctx=dctx).capture()
+                for i in range(3):
+                    gs(optimizer, *sring[i % n_ring])
+                barrier()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                for i in range(args.steps):
+                    gs(optimizer, *sring[i % n_ring])
+                s1.record()
+                barrier()
+                tt = torch.tensor([s0.elapsed_time(s1)], device=dev)
+                torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+                gms = float(tt) / args.steps
+                strong['cuda_graph'] = {'ms_per_step': gms, 'value': N_RAYS / (gms / 1e3)}
+                del gs
+            except Exception as e:          # a capture problem must not cost the bench line
+                strong['cuda_graph'] = {'error': f'{type(e).__name__}: {e}'[:200]}
 
     # ---- second half of BASELINE.json's metric: full 800x800 coarse+fine frames/s, pixel bands sharded over ranks
     render = None
