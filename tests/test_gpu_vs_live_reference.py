@@ -88,3 +88,28 @@ def test_post_process_on_device(ctx):
     rgb, disp, acc, wts, depth = eng.composite_forward(raw, zz, dd)
     assert float((rgb - outs[0]).abs().max()) <= 1e-6 and float((wts - outs[3]).abs().max()) <= 1e-6
     assert float((depth - outs[4]).abs().max()) <= 1e-5 and float((disp - outs[1]).abs().max()) <= 1e-6
+
+
+@pytest.mark.parametrize('n_rows,s_c,s_f', [(1000, 16, 32), (5000, 34, 64), (777, 100, 128), (4096, 128, 256), (40, 10, 16)])
+def test_sample_pdf_det_other_sizes_on_device(ctx, n_rows, s_c, s_f):
+    """The torch-CUDA summation order is restated for every row width below 128 (ATen picks block widths from the shape): other
+    N_samples_c than the shipped 64, checked against the reference's CUDA execution bit for bit."""
+    ref, eng, dev = ctx.ref, ctx.eng, ctx.dev
+    opts = SimpleNamespace(near=2., far=6., gpu_ids=[0], rank=0, N_samples_c=s_c, N_samples_f=s_f, perturb=0., chunk_pts=524288,
+                           chunk_rays=4096, data_type='blender')
+    gen = torch.Generator(device='cpu').manual_seed(1000 * s_c + n_rows)
+    z = torch.sort(torch.rand(n_rows, s_c, generator=gen) * 4 + 2, -1)[0].to(dev)
+    w = (torch.rand(n_rows, s_c, generator=gen) ** 6).to(dev)
+    mids = .5 * (z[..., 1:] + z[..., :-1])
+    rec = []
+    real = torch.searchsorted
+    with mock.patch('torch.searchsorted', lambda *a, **k: rec.append(real(*a, **k)) or rec[-1]):
+        s_ref = ref.proc.sample_pdf(mids, w[..., 1:-1], s_f, det=True, opts=opts)
+    ww = w[..., 1:-1] + 1e-5
+    pdf = ww / torch.sum(ww, -1, keepdim=True)
+    cdf_ref = torch.cat([torch.zeros_like(pdf[..., :1]), torch.cumsum(pdf, -1)], -1)
+    _, zs, inds, cdf = eng.sample_pdf(z, w, s_f, u=torch.linspace(0., 1., steps=s_f, device=dev), want_samples=True, want_inds=True,
+                                      want_cdf=True)
+    assert bits_differ(cdf, cdf_ref) == 0, (n_rows, s_c)
+    assert int((inds != rec[-1]).sum()) == 0
+    assert bits_differ(zs, s_ref) == 0
