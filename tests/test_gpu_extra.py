@@ -694,3 +694,47 @@ def test_batch_cursor_fast_path_equals_reference_protocol():
         o, d, c = b.next_batch(bs)
         assert torch.equal(torch.stack([o, d, c], 1), ref[k][0]) and b.epoch == ref[k][1], k
     assert b.epoch == 3 and torch.equal(b.rays_rgb, table)          # three reshuffles, the table itself untouched
+
+
+def test_adam_step_sum_equals_adam_on_the_summed_gradient():
+    """nb_adam_step_sum (the data-parallel update with the all-reduce folded into its load) on ONE GPU: k gradient buffers summed
+    in order == nb_adam_step on their sum, bit for bit; the sum is written back to g."""
+    from nerf_pytorch_paeng_b200.engine import get_engine
+    eng = get_engine(torch.device('cuda', 0))
+    n = 595844
+    gen = torch.Generator(device='cuda').manual_seed(1)
+    p0 = torch.randn(n, device='cuda', generator=gen)
+    gs = [torch.randn(n, device='cuda', generator=gen) * 1e-3 for _ in range(4)]
+    m0, v0 = torch.rand(n, device='cuda', generator=gen) * 1e-3, torch.rand(n, device='cuda', generator=gen) * 1e-6
+    total = ((gs[0] + gs[1]) + gs[2]) + gs[3]                    # rank order, like the kernel
+    pa, ma, va = p0.clone(), m0.clone(), v0.clone()
+    eng.adam_step(pa, total, ma, va, 3e-4, 7)
+    pb, mb, vb = p0.clone(), m0.clone(), v0.clone()
+    g_own = gs[1].clone()                                        # "this rank" is rank 1: its own buffer receives the sum
+    eng.adam_step_sum(pb, g_own, [gs[0], g_own, gs[2], gs[3]], mb, vb, 3e-4, 7)
+    torch.cuda.synchronize()
+    assert torch.equal(g_own, total)
+    assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb)
+
+
+def test_opts_precision_selects_the_mlp_path():
+    """config.py --precision / opts.precision is honoured by the drop-in entry points (the flag was dead)."""
+    from nerf_pytorch_paeng_b200 import config, nerf_process
+    from nerf_pytorch_paeng_b200._lib import NB_BF16, NB_FP32
+    from nerf_pytorch_paeng_b200.model import NeRF
+    assert config.get_args_parser([]).precision == 'bf16'                        # the drop-in default is the tensor-core path
+    g = load_golden('raygen.npz')
+    net = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).cuda()
+    assert net.model_fine.precision == NB_FP32                                      # a bare module starts on the parity path
+    rays = cu(np.concatenate([np.tile(g['rays_o8'][:1], (64, 1)), g['rays_d8'][:64]], -1))
+    for prec, code in (('bf16', NB_BF16), ('fp32', NB_FP32)):
+        opts = make_opts(precision=prec)
+        with torch.no_grad():
+            out = nerf_process.render_rays(rays, net, None, opts)
+        assert net.model_coarse.precision == code and net.model_fine.precision == code
+        assert bool(torch.isfinite(out['rgb_f']).all())
+    opts = make_opts()                                                             # no attribute: the module's setting is left alone
+    net.set_precision('bf16')
+    with torch.no_grad():
+        nerf_process.render_rays(rays, net, None, opts)
+    assert net.model_fine.precision == NB_BF16
