@@ -71,7 +71,8 @@ constexpr int kThreads = 576;   // warp 0 producer, warp 1 MMA, 8 epilogue warps
 constexpr int kEpiThreads = 256;
 constexpr int kBarEpi0 = 1;
 
-__constant__ TcSmall c_fw;   // small fp32 parameters of the network being run (see nb_mlp_tc.h)   // named barrier ids of the two epilogue groups
+__constant__ TcSmall c_fw[kConstBanks];   // small fp32 parameters of the network being run (see nb_mlp_tc.h), one bank per stream in flight (nb_cbank.h)
+NbConstBankTable g_fw_banks;   // named barrier ids of the two epilogue groups
 
 struct FwdParams {
   CUtensorMap tmap_w;     // pair mode only: packed forward blobs viewed as [rows, 64] bf16, box = 64 rows (8 KB), no swizzle (pre-swizzled images)
@@ -91,6 +92,7 @@ struct FwdParams {
   int dbg_step;
   long long* prof;        // optional per-CTA cycle counters [grid][8] (NB_TC_PROF diagnostic)
   int abl;                // ablation bits for profiling experiments (NB_TC_ABLATE env): 1 no masks, 2 no stash stores
+  int bank;               // which copy of c_fw holds this network's constants (nb_cbank.h)
 };
 
 // positional-encoding features of one 3-vector, written as bf16 into a swizzled 128-byte row.
@@ -157,7 +159,8 @@ __device__ __forceinline__ void emb_row_to_smem(uint32_t row_addr, uint32_t r, c
 template <bool TRAIN, bool DBG, int KIND>
 __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begin, int c_end, uint32_t t_addr, uint32_t act_base, uint32_t r,
                                            long long pt, bool valid, uint32_t* mdst, uint8_t* gdst, float& sigma, float (&rgb)[3]) {
-  const float* bias = c_fw.bias[s];
+  const TcSmall& C = c_fw[p.bank];
+  const float* bias = C.bias[s];
   uint4 mw = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 1
   for (int c32 = c_begin; c32 < c_end; ++c32) {
@@ -185,12 +188,12 @@ __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begi
       if (k == 0) mw.x = m; else if (k == 1) mw.y = m; else if (k == 2) mw.z = m; else mw.w = m;
     }
     if (KIND == 1) {            // sigma head on the fp32 post-ReLU trunk output (NeRF.py:43)
-      const float* w = c_fw.ws + c32 * 32;
+      const float* w = C.ws + c32 * 32;
 #pragma unroll
       for (int j = 0; j < 32; ++j) sigma = fmaf(fmaxf(v[j], 0.f), w[j], sigma);
     }
     if (KIND == 2) {            // rgb head on the fp32 post-ReLU view features (NeRF.py:50)
-      const float* w = c_fw.wc + c32 * 32;
+      const float* w = C.wc + c32 * 32;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float hj = fmaxf(v[j], 0.f);
@@ -459,8 +462,8 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
           if (half == 0 && valid) {
             float4 o;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(scratch));
-            reinterpret_cast<float4*>(p.raw)[pt] = make_float4(rgb[0] + o.x + c_fw.bc[0], rgb[1] + o.y + c_fw.bc[1],
-                                                               rgb[2] + o.z + c_fw.bc[2], sigma + o.w + c_fw.bc[3]);
+            reinterpret_cast<float4*>(p.raw)[pt] = make_float4(rgb[0] + o.x + c_fw[p.bank].bc[0], rgb[1] + o.y + c_fw[p.bank].bc[1],
+                                                               rgb[2] + o.z + c_fw[p.bank].bc[2], sigma + o.w + c_fw[p.bank].bc[3]);
           }
         }
       }
@@ -661,7 +664,9 @@ static int launch_fwd(nb_handle_t h, FwdParams& fp, bool train, cudaStream_t st)
     NB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     h->fwd_attr_done[ki] = true;
   }
-  NB_CUDA(h, cudaMemcpyToSymbolAsync(c_fw, fp.wpk + nb_tc_small_offset(), sizeof(TcSmall), 0, cudaMemcpyDeviceToDevice, st));
+  NB_CUDA(h, nb_const_bank_acquire(g_fw_banks, h->device, st, &fp.bank));
+  NB_CUDA(h, cudaMemcpyToSymbolAsync(c_fw, fp.wpk + nb_tc_small_offset(), sizeof(TcSmall), (size_t)fp.bank * sizeof(TcSmall),
+                                     cudaMemcpyDeviceToDevice, st));
   const long long n_tiles = (fp.P + 127) / 128;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

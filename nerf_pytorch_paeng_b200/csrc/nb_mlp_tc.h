@@ -2,6 +2,7 @@
 #pragma once
 #include <functional>
 #include "nb_mlp.h"
+#include "nb_cbank.h"
 
 constexpr uint32_t kBlobBytes = 16384;   // one K-block of a 128-point tile: 128 points x 64 bf16 (shared memory: 128B-swizzled K-major rows;
                                          // stash / dY blobs in HBM: chunk-major, stash_off() in nb_tc_common.cuh)

@@ -63,7 +63,8 @@ constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;
 constexpr int kThreads = 576;      // warp 0 producer, warp 1 MMA, 8 epilogue warps per slot (two per TMEM lane quarter: column halves)
 constexpr int kEpi = 256;
 
-__constant__ TcSmall c_bw;   // small fp32 parameters (sigma / rgb head weights) of the network being differentiated
+__constant__ TcSmall c_bw[kConstBanks];   // small fp32 parameters (sigma / rgb head weights) of the network being differentiated, one bank per stream in flight
+NbConstBankTable g_bw_banks;
 
 struct DgradParams {
   long long P;
@@ -76,6 +77,7 @@ struct DgradParams {
   uint8_t* ws;              // dY blobs out
   BwdWs w;
   int abl;                  // NB_TC_ABLATE experiments: 64 = dY tiles written to an L2-resident window
+  int bank;                 // which copy of c_bw holds this network's constants (nb_cbank.h)
 };
 
 // MC: clusters of two CTAs sharing the W^T stream by multicast (see mlp_fwd_chain_kernel)
@@ -204,7 +206,7 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int col = c * 8 + j;
-          const float val = fmaf(dr.x, c_bw.wc[col], fmaf(dr.y, c_bw.wc[128 + col], dr.z * c_bw.wc[256 + col]));
+          const float val = fmaf(dr.x, c_bw[p.bank].wc[col], fmaf(dr.y, c_bw[p.bank].wc[128 + col], dr.z * c_bw[p.bank].wc[256 + col]));
           const uint32_t gmsel = (c & 8) ? ((c & 4) ? gmw[3] : gmw[2]) : ((c & 4) ? gmw[1] : gmw[0]);
           v[j] = ((gmsel >> (31 - (col & 31))) & 1u) ? 0.f : val;
         }
@@ -244,7 +246,7 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
           tmem_ld32(t_addr + (uint32_t)c32 * 32u, v);
           tmem_ld_wait();
           if (b == 0) {   // density head: d h7 += d sigma * W_sigma   (NeRF.py:43)
-            const float* w = c_bw.ws + c32 * 32;
+            const float* w = c_bw[p.bank].ws + c32 * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaf(dr.w, w[j], v[j]);
           }
@@ -304,16 +306,24 @@ struct WgradJob {
   float* sig_out;
   float* sig_bias;
   int weight;            // operand blobs streamed per unit (64 points)
+  int n_stages;          // ring stages for this job: min(kWgMaxStages, kWgRingBytes / stage bytes)
   long long work_begin;  // sum of weight * n_units over the preceding jobs
 };
-struct WgradParams { WgradJob job[kMaxJobs]; int n_jobs; long long n_tiles; long long n_points; long long total_work; int abl; };
+struct WgradParams { WgradJob job[kMaxJobs]; int n_jobs; long long n_tiles; long long n_points; long long total_work; int abl;
+                     unsigned long long* prof; };   // prof: optional [grid][4] ns time stamps (NB_TC_PROF diagnostic)
 
 constexpr int kWgThreads = 192;                         // warp0 producer, warp1 MMA, warps 2-5 bias sums + epilogue
-constexpr int kWgStages = 3;
-constexpr uint32_t kWgStageBytes = 8 * 8192;            // up to 4 A + 4 B half-blobs (64 points x 128 B)
-constexpr uint32_t kWgOffBar = kWgStages * kWgStageBytes;
-constexpr uint32_t kWgOffSig = kWgOffBar + 256;         // [kWgStages][64] fp32 d_sigma of the stage's points
-constexpr uint32_t kWgSmemBytes = kWgOffSig + kWgStages * 256 + 1024;
+// Operand ring: 224 KB cut into as many stages as fit the job's unit (4..8 half blobs of 8 KB = 64 points of every operand): 3 stages of
+// 64 KB for the trunk layers, 4 x 56 KB for the folded view layer, 5 x 40 KB for the two PE(x) jobs, 6 x 32 KB for the rgb head.  What
+// a CTA gets of the HBM stream follows the bytes it keeps in flight (measured: with 3 stages for every job the CTAs of the 32 / 40 KB
+// jobs took 1.29 ms for the same byte count the 64 KB jobs streamed in 0.96 ms, and the kernel ends with its slowest CTA), so every
+// job keeps ~200 KB in flight whatever its unit size.
+constexpr int kWgMaxStages = 6;
+constexpr uint32_t kWgRingBytes = 224 * 1024;
+constexpr uint32_t kWgOffBar = kWgRingBytes;            // full[6] | empty[6] (+64) | done (+128) | tmem slot (+136) | free (+144)
+constexpr uint32_t kWgOffSig = kWgOffBar + 256;         // [kWgMaxStages][64] fp32 d_sigma of the stage's points
+constexpr uint32_t kWgSmemBytes = kWgOffSig + kWgMaxStages * 256 + 1024;
+static_assert(kWgSmemBytes <= 232448, "wgrad ring exceeds the 227 KB of shared memory a CTA can have");
 
 // One CTA's share of a job: the kernel's work is the concatenation over jobs of n_units units costing `weight` (operand
 // blobs per unit) each; CTA c owns the slice [total*c/G, total*(c+1)/G) of that line and a unit belongs to the CTA that
@@ -335,14 +345,14 @@ mlp_wgrad_kernel(const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_bar = sbase + kWgOffBar;
-  const uint32_t b_full = s_bar, b_empty = s_bar + 32, b_done = s_bar + 64, s_tmem = s_bar + 72, b_free = s_bar + 80;
+  const uint32_t b_full = s_bar, b_empty = s_bar + 64, b_done = s_bar + 128, s_tmem = s_bar + 136, b_free = s_bar + 144;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long n_units = p.n_tiles * 2;          // units of work: half tiles (64 points); unit u -> tile u>>1, half u&1
   const long long lo = p.total_work * (long long)blockIdx.x / (long long)gridDim.x;
   const long long hi = p.total_work * ((long long)blockIdx.x + 1) / (long long)gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kWgStages; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1 + 4); }
+    for (int i = 0; i < kWgMaxStages; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1 + 4); }
     mbar_init(b_done, 1);
     mbar_init(b_free, 4);
     fence_barrier_init();
@@ -353,23 +363,37 @@ mlp_wgrad_kernel(const WgradParams p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
+  auto stamp = [&](int k) {
+    if (p.prof) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.prof[(size_t)blockIdx.x * 4 + k] = t; }
+  };
+  if (threadIdx.x == 0) stamp(0);
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      // Every barrier keeps its own phase parity (bit i of the mask = parity to wait for at the next use of stage i), because the
+      // number of stages in use changes from job to job.  Before the first load of a CTA's next job the ring is drained: the new
+      // job's stage slots have another size and would overlap slots the MMAs may still be reading.
+      uint32_t pmask = (1u << kWgMaxStages) - 1u;
+      bool first_seg = true;
       for (int j = 0; j < p.n_jobs; ++j) {
         long long u0, u1;
         if (!wg_segment(p, j, lo, hi, n_units, u0, u1)) continue;
         const WgradJob& J = p.job[j];
         const uint32_t stage_bytes = (uint32_t)(J.m_blk + J.n_blk + J.n2_blk) * 8192u;
+        const uint32_t ns = (uint32_t)J.n_stages;
+        if (!first_seg)
+          for (int i = 0; i < kWgMaxStages; ++i) mbar_wait(b_empty + 8 * i, (pmask >> i) & 1u);
+        first_seg = false;
+        uint32_t stage = 0;
         for (long long u = u0; u < u1; ++u) {
           const long long tile = u >> 1;
           const long long tile_a = (p.abl & 64) ? (tile & 63) : tile;      // experiments: operands from an L2-resident window
           const long long tile_b = (p.abl & 128) ? (tile & 63) : tile;
           const uint32_t half = (uint32_t)(u & 1) * 8192u;
-          mbar_wait(b_empty + 8 * stage, phase ^ 1);
+          mbar_wait(b_empty + 8 * stage, (pmask >> stage) & 1u);
+          pmask ^= 1u << stage;
           mbar_expect_tx(b_full + 8 * stage, stage_bytes);
-          const uint32_t dst = sbase + stage * kWgStageBytes;
+          const uint32_t dst = sbase + stage * stage_bytes;
           for (int k = 0; k < J.m_blk; ++k)
             bulk_g2s(dst + (uint32_t)k * 8192u, J.a + ((size_t)tile_a * J.a_blobs + J.a_first + k) * kBlobBytes + half, 8192u, b_full + 8 * stage);
           for (int k = 0; k < J.n_blk; ++k)
@@ -378,27 +402,32 @@ mlp_wgrad_kernel(const WgradParams p) {
           for (int k = 0; k < J.n2_blk; ++k)
             bulk_g2s(dst + (uint32_t)(J.m_blk + J.n_blk + k) * 8192u, J.b2 + ((size_t)tile_b * J.b2_blobs + J.b2_first + k) * kBlobBytes + half,
                      8192u, b_full + 8 * stage);
-          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+          if (++stage == ns) stage = 0;
         }
       }
+      stamp(1);      // last load issued
     }
   } else if (warp == 1) {
-    uint32_t stage = 0, phase = 0, seg = 0;
+    uint32_t cmask = 0, seg = 0;
     for (int j = 0; j < p.n_jobs; ++j) {
       long long u0, u1;
       if (!wg_segment(p, j, lo, hi, n_units, u0, u1)) continue;
       const WgradJob& J = p.job[j];
+      const uint32_t stage_bytes = (uint32_t)(J.m_blk + J.n_blk + J.n2_blk) * 8192u, ns = (uint32_t)J.n_stages;
+      uint32_t stage = 0;
       const uint32_t idesc = umma_idesc(128, 64 * J.n_blk, 1, 1);      // both operands MN-major
       const uint32_t idesc2 = umma_idesc(128, J.n2_blk > 0 ? 64 * J.n2_blk : 64, 1, 1);
       const int m_halves = J.m_blk >> 1;
       if (seg > 0) { mbar_wait(b_free, (seg - 1) & 1); tc_fence_after(); }    // previous segment's accumulator has been drained
       for (long long u = u0; u < u1; ++u) {
-        mbar_wait(b_full + 8 * stage, phase);
+        mbar_wait(b_full + 8 * stage, (cmask >> stage) & 1u);
+        cmask ^= 1u << stage;
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_addr = sbase + stage * kWgStageBytes;
+          const uint32_t a_addr = sbase + stage * stage_bytes;
           const uint32_t b_addr = a_addr + (uint32_t)J.m_blk * 8192u;
           const uint32_t first = (u == u0) ? 0u : 1u;
+          if (!(p.abl & 512)) {      // 512: timing experiment without the MMAs (stages are released at once)
           // operands: half blobs [feature/8][64 points][8 features] laid end to end => atoms of 8 features every 1024 B (SBO),
           // 8-point groups every 128 B (LBO), a K16 slice every 256 B; 128 output rows (one m_half) = 16 atoms = 16 KB further
           for (int mh = 0; mh < m_halves; ++mh) {
@@ -414,14 +443,16 @@ mlp_wgrad_kernel(const WgradParams p) {
               umma_ss(tmem_base + 256u, umma_desc_mn_noswz(a_addr + k16 * 256u, 128, 1024), umma_desc_mn_noswz(b2_addr + k16 * 256u, 128, 1024),
                       idesc2, (first | (uint32_t)k16) ? 1u : 0u);
           }
+          }
           umma_commit(b_empty + 8 * stage);
           if (u == u1 - 1) umma_commit(b_done);
         }
         __syncwarp();
-        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        if (++stage == ns) stage = 0;
       }
       ++seg;
     }
+    if (lane == 0) stamp(2);      // last MMA issued
   } else {
     // ---- column sums (bias gradients, density-head rider) from the staged operands, then the TMEM -> global flush ----
     // staged operand = consecutive 1 KB atoms [64 points][8 features].  Eight consecutive lanes read 8 consecutive points of ONE atom
@@ -431,29 +462,37 @@ mlp_wgrad_kernel(const WgradParams p) {
     const int j8 = t & 7;                     // point j8 + 8*i of the stage
     const int q16 = t >> 3;                   // 16 groups of 8 lanes: group g owns atoms g and g+16
     const uint32_t q = (uint32_t)warp & 3u;   // TMEM lane quarter of this warp
-    uint32_t stage = 0, phase = 0, seg = 0;
+    uint32_t cmask = 0, seg = 0;
     for (int j = 0; j < p.n_jobs; ++j) {
       long long u0, u1;
       if (!wg_segment(p, j, lo, hi, n_units, u0, u1)) continue;
       const WgradJob& J = p.job[j];
+      const uint32_t stage_bytes = (uint32_t)(J.m_blk + J.n_blk + J.n2_blk) * 8192u, ns = (uint32_t)J.n_stages;
+      uint32_t stage = 0;
       const int a_atoms = 8 * J.m_blk;                      // dY operand: 16 or 32 atoms
-      const bool do_bias = J.bias_out != nullptr;
-      const bool do_sig = J.sig_draw != nullptr;            // rider on the B operand (N = 256 = 32 atoms)
+      const bool do_bias = J.bias_out != nullptr && !(p.abl & 256);      // 256: timing experiment without the column sums
+      const bool do_sig = J.sig_draw != nullptr && !(p.abl & 256);       // rider on the B operand (N = 256 = 32 atoms)
       float bs[2][8], sg[2][8], sgb = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) { bs[0][k] = bs[1][k] = 0.f; sg[0][k] = sg[1][k] = 0.f; }
-      float ds_next = 0.f;
-      if (do_sig && t < 64) { const long long pt = u0 * 64 + t; ds_next = pt < p.n_points ? J.sig_draw[pt * 4 + 3] : 0.f; }
+      // d_sigma of the units ahead, fetched TWO units early: under a saturated HBM stream a global load takes longer than one stage lasts
+      float ds_next = 0.f, ds_next2 = 0.f;
+      auto load_ds = [&](long long u) -> float {
+        const long long pt = u * 64 + t;
+        return (u < u1 && pt < p.n_points) ? J.sig_draw[pt * 4 + 3] : 0.f;
+      };
+      if (do_sig && t < 64) { ds_next = load_ds(u0); ds_next2 = load_ds(u0 + 1); }
       for (long long u = u0; u < u1; ++u) {
         const uint32_t sig = sbase + kWgOffSig + stage * 256u;
         if (do_sig) {
-          // d_sigma of this stage's 64 points -> shared (rows past the last point contribute nothing); next unit's prefetched
+          // d_sigma of this stage's 64 points -> shared (rows past the last point contribute nothing)
           if (t < 64) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sig + (uint32_t)t * 4u), "f"(ds_next) : "memory");
           named_bar_sync(1, 128);
-          if (t < 64 && u + 1 < u1) { const long long pt = (u + 1) * 64 + t; ds_next = pt < p.n_points ? J.sig_draw[pt * 4 + 3] : 0.f; }
+          if (t < 64) { ds_next = ds_next2; ds_next2 = load_ds(u + 2); }
         }
-        mbar_wait(b_full + 8 * stage, phase);
-        const uint32_t st_base = sbase + stage * kWgStageBytes;
+        mbar_wait(b_full + 8 * stage, (cmask >> stage) & 1u);
+        cmask ^= 1u << stage;
+        const uint32_t st_base = sbase + stage * stage_bytes;
         if (do_bias) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -492,7 +531,7 @@ mlp_wgrad_kernel(const WgradParams p) {
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(b_empty + 8 * stage);
-        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        if (++stage == ns) stage = 0;
       }
       // combine the eight point-interleaved partial sums of every atom (lanes j8 = 0..7), then lane j8 adds column j8 of the atom
       if (do_bias || do_sig) {
@@ -578,6 +617,7 @@ mlp_wgrad_kernel(const WgradParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(3);   // accumulators flushed
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -665,8 +705,9 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
     dp.P = P; dp.wpk = (const uint8_t*)packed + nb_tc_fwd_packed_bytes(); dp.prm = params; dp.L = L; dp.d_raw = d_raw;
     dp.stash = (const uint8_t*)act_save; dp.st = S; dp.ws = (uint8_t*)ws; dp.w = W;
     { const char* e = getenv("NB_TC_ABLATE"); dp.abl = e ? atoi(e) : 0; }   // timing experiments only
-    NB_CUDA(h, cudaMemcpyToSymbolAsync(c_bw, (const uint8_t*)packed + nb_tc_small_offset(), sizeof(TcSmall), 0,
-                                       cudaMemcpyDeviceToDevice, st));
+    NB_CUDA(h, nb_const_bank_acquire(g_bw_banks, h->device, st, &dp.bank));
+    NB_CUDA(h, cudaMemcpyToSymbolAsync(c_bw, (const uint8_t*)packed + nb_tc_small_offset(), sizeof(TcSmall),
+                                       (size_t)dp.bank * sizeof(TcSmall), cudaMemcpyDeviceToDevice, st));
     static int mode_env = -1;
     if (mode_env < 0) { const char* e = getenv("NB_TC_CLUSTER"); mode_env = e ? atoi(e) : 2; }
     cudaLaunchConfig_t cfg;
@@ -738,12 +779,41 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
     wp.n_points = P;
     // every CTA streams an equal slice of the concatenated job list (wg_segment)
     long long work = 0;
-    for (int j = 0; j < nj; ++j) { wp.job[j].weight = weight[j]; wp.job[j].work_begin = work; work += (long long)weight[j] * n_tiles * 2; }
+    for (int j = 0; j < nj; ++j) {
+      wp.job[j].weight = weight[j]; wp.job[j].work_begin = work; work += (long long)weight[j] * n_tiles * 2;
+      const int fit = (int)(kWgRingBytes / ((uint32_t)weight[j] * 8192u));
+      wp.job[j].n_stages = fit > kWgMaxStages ? kWgMaxStages : fit;
+    }
     wp.total_work = work;
     int begin = h->sm_count;
     if ((long long)begin > n_tiles * 2) begin = (int)(n_tiles * 2);
+    static unsigned long long* prof_dev = nullptr;
+    const bool prof = getenv("NB_TC_PROF") != nullptr;
+    if (prof) {
+      if (!prof_dev) cudaMalloc(&prof_dev, 256 * 4 * sizeof(unsigned long long));
+      cudaMemsetAsync(prof_dev, 0, 256 * 4 * sizeof(unsigned long long), st);
+      wp.prof = prof_dev;
+    }
     mlp_wgrad_kernel<<<begin, kWgThreads, kWgSmemBytes, st>>>(wp);
     NB_LAUNCHED(h);
+    if (prof) {   // diagnostic only: synchronous read-back of the per-CTA time stamps (ns since the earliest CTA start)
+      static unsigned long long host[256 * 4];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(host, prof_dev, sizeof(host), cudaMemcpyDeviceToHost);
+      unsigned long long t0 = ~0ull;
+      for (int b = 0; b < begin; ++b) if (host[b * 4] < t0) t0 = host[b * 4];
+      fprintf(stderr, "nb_tc wgrad prof P=%lld grid=%d (cta: first job, last job | start, last load issued, last MMA issued, flushed [us])\n", (long long)P, begin);
+      for (int b = 0; b < begin; ++b) {
+        const long long lo = work * b / begin, hi = work * (b + 1) / begin;
+        int j0 = -1, j1 = -1;
+        for (int j = 0; j < nj; ++j) {
+          const long long jb = wp.job[j].work_begin, je = jb + (long long)wp.job[j].weight * n_tiles * 2;
+          if (lo < je && hi > jb) { if (j0 < 0) j0 = j; j1 = j; }
+        }
+        fprintf(stderr, "  cta %3d: jobs %2d..%2d | %7.1f %7.1f %7.1f %7.1f\n", b, j0, j1, (host[b * 4] - t0) * 1e-3, (host[b * 4 + 1] - t0) * 1e-3,
+                (host[b * 4 + 2] - t0) * 1e-3, (host[b * 4 + 3] - t0) * 1e-3);
+      }
+    }
     fold_grads_kernel<<<256 + 128 + 1, 256, 0, st>>>(params, L, fold_g, grad);
     NB_LAUNCHED(h);
   }

@@ -738,3 +738,40 @@ def test_opts_precision_selects_the_mlp_path():
     with torch.no_grad():
         nerf_process.render_rays(rays, net, None, opts)
     assert net.model_fine.precision == NB_BF16
+
+
+def test_bf16_mlp_calls_on_concurrent_streams():
+    """The bf16 MLP entries stage per-network constants in __constant__ memory; a bank per stream in flight (nb_cbank.h) makes calls
+    for DIFFERENT networks on different streams safe (one stream per device at a time).  Two, then six streams
+    (more than there are banks: the least recently used one is handed over) run the coarse and the fine network interleaved; every
+    result equals the single-stream result bit for bit."""
+    from nerf_pytorch_paeng_b200.model import NeRF
+    torch.manual_seed(3)
+    net = NeRF(8, 256, 63, 27, [4], gt_camera_param=(None, None)).cuda()
+    with torch.no_grad():
+        for m in (net.model_coarse, net.model_fine):
+            for lin in list(m.linear_x) + [m.linear_feat, m.linear_d, m.linear_density, m.linear_color]:
+                lin.bias.uniform_(-0.5, 0.5)                               # the constants that would be mixed up
+    net.set_precision('bf16')
+    g = load_golden('raygen.npz')
+    n, s = 1024, 192                                                        # 196,608 points: a few hundred microseconds per call
+    rs = np.random.RandomState(0)
+    rays = cu(np.concatenate([np.tile(g['rays_o8'][:1], (n, 1)), g['rays_d8'][:n]], -1))
+    z = cu(np.sort(rs.rand(n, s).astype(np.float32) * 4 + 2, -1))
+    mods = (net.model_coarse, net.model_fine)
+    with torch.no_grad():
+        want = [m.forward_rays(rays, z).clone() for m in mods]
+        for m in mods:
+            m.packed_weights()                                              # packed once, outside the streams
+    torch.cuda.synchronize()
+    assert not torch.equal(want[0], want[1])
+    for n_streams in (2, 6):
+        streams = [torch.cuda.Stream() for _ in range(n_streams)]
+        got = []
+        for it in range(4 * n_streams):
+            k = it % n_streams
+            with torch.cuda.stream(streams[k]), torch.no_grad():
+                got.append(((it + it // n_streams) % 2, mods[(it + it // n_streams) % 2].forward_rays(rays, z)))
+        torch.cuda.synchronize()
+        for which, out in got:
+            assert torch.equal(out, want[which]), (n_streams, which)
