@@ -407,9 +407,9 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
         const float ox = rr[0], oy = rr[1], oz = rr[2], dx = rr[3], dy = rr[4], dz = rr[5];
         const float inv = rsqrtf(dx * dx + dy * dy + dz * dz);
         dirx = dx * inv; diry = dy * inv; dirz = dz * inv;
-        pe_row_to_smem<10>(aux_base + r * 128u, r, fmaf(dx, zz, ox), fmaf(dy, zz, oy), fmaf(dz, zz, oz), false, half * 4, half * 4 + 4, g_embx);
+        pe_row_to_smem<10>(aux_base + r * 128u, r, fmaf(dx, zz, ox), fmaf(dy, zz, oy), fmaf(dz, zz, oz), TRAIN, half * 4, half * 4 + 4, g_embx);
       } else {
-        emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x, 63, false, half * 4, half * 4 + 4, g_embx);
+        emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x, 63, TRAIN, half * 4, half * 4 + 4, g_embx);
       }
       fence_proxy_async_smem();
       if (CTA2) mbar_arrive_cluster(a_ready_addr); else mbar_arrive(b_aready + 8 * slot);
@@ -448,8 +448,8 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(scratch), "f"(rgb[0]), "f"(rgb[1]), "f"(rgb[2]), "f"(sigma) : "memory");
         if (s == 5) {
           // the view-layer operand needs PE(viewdir) in aux; aux (PE of the point) was last read by MMA step 5, now retired
-          if (p.x_emb == nullptr) pe_row_to_smem<4>(aux_base + r * 128u, r, dirx, diry, dirz, false, half * 4, half * 4 + 4, g_embd);
-          else emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x + 63, 27, false, half * 4, half * 4 + 4, g_embd);
+          if (p.x_emb == nullptr) pe_row_to_smem<4>(aux_base + r * 128u, r, dirx, diry, dirz, TRAIN, half * 4, half * 4 + 4, g_embd);
+          else emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x + 63, 27, TRAIN, half * 4, half * 4 + 4, g_embd);
         }
         fence_proxy_async_smem();
         tc_fence_before();

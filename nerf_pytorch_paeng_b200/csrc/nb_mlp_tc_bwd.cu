@@ -294,6 +294,8 @@ struct WgradJob {
   float* out;            // dW + column offset, row-major [rows, ld]
   int ld, m_first, m_valid, n_valid;   // rows [m_first, m_valid) x cols [0, n_valid) are written; row m -> out + (m - m_first)*ld
   float* bias_out;       // dY column sums of columns [m_first, m_valid) or nullptr
+  int bias_col, bias_reg; // bias_col >= 0: column of accumulator region bias_reg (1 = B, 2 = B2) whose B feature is the constant 1.0, i.e. the
+                         // tensor cores already produce the column sums there; < 0: summed from the staged operand on the CUDA cores
   // optional second B operand sharing the same A (view layer: [features | PE(viewdir)]): N2 = 64*n2_blk, accumulated in
   // TMEM columns 256.. (needs m_blk == 2), written to out2
   const uint8_t* b2;
@@ -312,7 +314,7 @@ struct WgradJob {
 struct WgradParams { WgradJob job[kMaxJobs]; int n_jobs; long long n_tiles; long long n_points; long long total_work; int abl;
                      unsigned long long* prof; };   // prof: optional [grid][4] ns time stamps (NB_TC_PROF diagnostic)
 
-constexpr int kWgThreads = 192;                         // warp0 producer, warp1 MMA, warps 2-5 bias sums + epilogue
+constexpr int kWgThreads = 320;                         // warp0 producer, warp1 MMA, warps 2-9 column sums + accumulator flush
 // Operand ring: 224 KB cut into as many stages as fit the job's unit (4..8 half blobs of 8 KB = 64 points of every operand): 3 stages of
 // 64 KB for the trunk layers, 4 x 56 KB for the folded view layer, 5 x 40 KB for the two PE(x) jobs, 6 x 32 KB for the rgb head.  What
 // a CTA gets of the HBM stream follows the bytes it keeps in flight (measured: with 3 stages for every job the CTAs of the 32 / 40 KB
@@ -352,9 +354,9 @@ mlp_wgrad_kernel(const WgradParams p) {
   const long long hi = p.total_work * ((long long)blockIdx.x + 1) / (long long)gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kWgMaxStages; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1 + 4); }
+    for (int i = 0; i < kWgMaxStages; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1 + 8); }
     mbar_init(b_done, 1);
-    mbar_init(b_free, 4);
+    mbar_init(b_free, 8);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, 512);
@@ -454,14 +456,19 @@ mlp_wgrad_kernel(const WgradParams p) {
     }
     if (lane == 0) stamp(2);      // last MMA issued
   } else {
-    // ---- column sums (bias gradients, density-head rider) from the staged operands, then the TMEM -> global flush ----
-    // staged operand = consecutive 1 KB atoms [64 points][8 features].  Eight consecutive lanes read 8 consecutive points of ONE atom
-    // (128 contiguous bytes: conflict-free), so a lane accumulates partial column sums over the points j, j+8, .. of its atoms; the
-    // eight partial sums are combined by shuffles once per job segment.
-    const int t = threadIdx.x - 64;           // 0..127
+    // ---- column sums (bias gradients, density-head rider) from the staged operands, then the TMEM -> global flush: EIGHT warps ----
+    // (two per scheduler: with one warp per scheduler the dependent unpack / add chains ran at ~0.25 IPC and the jobs with the most
+    // sums per byte -- the PE(x) jobs and the folded view layer -- released their stages late: their CTAs finished 7-12 % after the
+    // others.)  Staged operand = consecutive 1 KB atoms [64 points][8 features].  Eight consecutive lanes read 8 consecutive points
+    // of ONE atom (128 contiguous bytes: conflict-free), so a lane accumulates partial column sums over the points j8, j8+8, .. of
+    // its atom; the eight partial sums are combined by shuffles once per job segment.  Jobs whose B operand carries a constant 1.0
+    // column (the pad column of PE(x) / PE(viewdir), written by the training forward) get their dY column sums from the TENSOR
+    // CORES instead: that accumulator column IS sum_p dY[p][m] (bias_col >= 0), and the flush adds it to the bias gradient.
+    const int t = threadIdx.x - 64;           // 0..255
     const int j8 = t & 7;                     // point j8 + 8*i of the stage
-    const int q16 = t >> 3;                   // 16 groups of 8 lanes: group g owns atoms g and g+16
-    const uint32_t q = (uint32_t)warp & 3u;   // TMEM lane quarter of this warp
+    const int q32 = t >> 3;                   // 32 groups of 8 lanes: group g owns atom g
+    const uint32_t q = (uint32_t)warp & 3u;   // TMEM lane quarter this warp may read
+    const uint32_t csel = ((uint32_t)warp - 2u) >> 2;     // the two warps of a quarter take alternate 32-column chunks of the flush
     uint32_t cmask = 0, seg = 0;
     for (int j = 0; j < p.n_jobs; ++j) {
       long long u0, u1;
@@ -470,104 +477,92 @@ mlp_wgrad_kernel(const WgradParams p) {
       const uint32_t stage_bytes = (uint32_t)(J.m_blk + J.n_blk + J.n2_blk) * 8192u, ns = (uint32_t)J.n_stages;
       uint32_t stage = 0;
       const int a_atoms = 8 * J.m_blk;                      // dY operand: 16 or 32 atoms
-      const bool do_bias = J.bias_out != nullptr && !(p.abl & 256);      // 256: timing experiment without the column sums
+      const bool do_bias = J.bias_out != nullptr && J.bias_col < 0 && !(p.abl & 256);      // 256: timing experiment without the sums
       const bool do_sig = J.sig_draw != nullptr && !(p.abl & 256);       // rider on the B operand (N = 256 = 32 atoms)
-      float bs[2][8], sg[2][8], sgb = 0.f;
+      float bs[8], sg[8], sgb = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { bs[0][k] = bs[1][k] = 0.f; sg[0][k] = sg[1][k] = 0.f; }
-      // d_sigma of the units ahead, fetched TWO units early: under a saturated HBM stream a global load takes longer than one stage lasts
-      float ds_next = 0.f, ds_next2 = 0.f;
-      auto load_ds = [&](long long u) -> float {
+      for (int k = 0; k < 8; ++k) { bs[k] = 0.f; sg[k] = 0.f; }
+      // d_sigma of the stage's 64 points travels global -> shared by 4-byte cp.async, issued TWO units ahead into a ring of four
+      // 256-byte slots (under a saturated HBM stream a global load outlasts a stage, and a register prefetch would stall the warp at
+      // its first use); points past the end are zero-filled (src-size 0) and contribute nothing
+      auto issue_ds = [&](long long u) {
         const long long pt = u * 64 + t;
-        return (u < u1 && pt < p.n_points) ? J.sig_draw[pt * 4 + 3] : 0.f;
+        const bool ok = u < u1 && pt < p.n_points;
+        const float* src = J.sig_draw + (ok ? pt * 4 + 3 : 3);
+        const uint32_t dst = sbase + kWgOffSig + (uint32_t)((u - u0) & 3) * 256u + (uint32_t)t * 4u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4u : 0u) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
       };
-      if (do_sig && t < 64) { ds_next = load_ds(u0); ds_next2 = load_ds(u0 + 1); }
+      if (do_sig && t < 64) { issue_ds(u0); issue_ds(u0 + 1); }
       for (long long u = u0; u < u1; ++u) {
-        const uint32_t sig = sbase + kWgOffSig + stage * 256u;
+        const uint32_t sig = sbase + kWgOffSig + (uint32_t)((u - u0) & 3) * 256u;
         if (do_sig) {
-          // d_sigma of this stage's 64 points -> shared (rows past the last point contribute nothing)
-          if (t < 64) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sig + (uint32_t)t * 4u), "f"(ds_next) : "memory");
-          named_bar_sync(1, 128);
-          if (t < 64) { ds_next = ds_next2; ds_next2 = load_ds(u + 2); }
+          if (t < 64) {
+            issue_ds(u + 2);                                              // slot of unit u-2: every thread is past its reads (barrier of u-1)
+            asm volatile("cp.async.wait_group 2;" ::: "memory");          // this unit's values have landed
+          }
+          named_bar_sync(1, kWgThreads - 64);
         }
         mbar_wait(b_full + 8 * stage, (cmask >> stage) & 1u);
         cmask ^= 1u << stage;
         const uint32_t st_base = sbase + stage * stage_bytes;
-        if (do_bias) {
+        if (do_bias && q32 < a_atoms) {
+          const uint32_t base = st_base + (uint32_t)q32 * 1024u + (uint32_t)j8 * 16u;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int atom = q16 + 16 * h;
-            if (atom < a_atoms) {
-              const uint32_t base = st_base + (uint32_t)atom * 1024u + (uint32_t)j8 * 16u;
-#pragma unroll 4
-              for (uint32_t i = 0; i < 8; ++i) {
-                uint32_t w0, w1, w2, w3;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + i * 128u));
-                bs[h][0] += __uint_as_float(w0 << 16); bs[h][1] += __uint_as_float(w0 & 0xFFFF0000u);
-                bs[h][2] += __uint_as_float(w1 << 16); bs[h][3] += __uint_as_float(w1 & 0xFFFF0000u);
-                bs[h][4] += __uint_as_float(w2 << 16); bs[h][5] += __uint_as_float(w2 & 0xFFFF0000u);
-                bs[h][6] += __uint_as_float(w3 << 16); bs[h][7] += __uint_as_float(w3 & 0xFFFF0000u);
-              }
-            }
+          for (uint32_t i = 0; i < 8; ++i) {
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + i * 128u));
+            bs[0] += __uint_as_float(w0 << 16); bs[1] += __uint_as_float(w0 & 0xFFFF0000u);
+            bs[2] += __uint_as_float(w1 << 16); bs[3] += __uint_as_float(w1 & 0xFFFF0000u);
+            bs[4] += __uint_as_float(w2 << 16); bs[5] += __uint_as_float(w2 & 0xFFFF0000u);
+            bs[6] += __uint_as_float(w3 << 16); bs[7] += __uint_as_float(w3 & 0xFFFF0000u);
           }
         }
         if (do_sig) {
+          const uint32_t base = st_base + (uint32_t)(a_atoms + q32) * 1024u + (uint32_t)j8 * 16u;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t base = st_base + (uint32_t)(a_atoms + q16 + 16 * h) * 1024u + (uint32_t)j8 * 16u;
-#pragma unroll 4
-            for (uint32_t i = 0; i < 8; ++i) {
-              uint32_t w0, w1, w2, w3;
-              float ds;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + i * 128u));
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ds) : "r"(sig + ((uint32_t)j8 + 8u * i) * 4u));
-              sg[h][0] = fmaf(ds, __uint_as_float(w0 << 16), sg[h][0]); sg[h][1] = fmaf(ds, __uint_as_float(w0 & 0xFFFF0000u), sg[h][1]);
-              sg[h][2] = fmaf(ds, __uint_as_float(w1 << 16), sg[h][2]); sg[h][3] = fmaf(ds, __uint_as_float(w1 & 0xFFFF0000u), sg[h][3]);
-              sg[h][4] = fmaf(ds, __uint_as_float(w2 << 16), sg[h][4]); sg[h][5] = fmaf(ds, __uint_as_float(w2 & 0xFFFF0000u), sg[h][5]);
-              sg[h][6] = fmaf(ds, __uint_as_float(w3 << 16), sg[h][6]); sg[h][7] = fmaf(ds, __uint_as_float(w3 & 0xFFFF0000u), sg[h][7]);
-              if (h == 0 && q16 == 0) sgb += ds;
-            }
+          for (uint32_t i = 0; i < 8; ++i) {
+            uint32_t w0, w1, w2, w3;
+            float ds;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + i * 128u));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ds) : "r"(sig + ((uint32_t)j8 + 8u * i) * 4u));
+            sg[0] = fmaf(ds, __uint_as_float(w0 << 16), sg[0]); sg[1] = fmaf(ds, __uint_as_float(w0 & 0xFFFF0000u), sg[1]);
+            sg[2] = fmaf(ds, __uint_as_float(w1 << 16), sg[2]); sg[3] = fmaf(ds, __uint_as_float(w1 & 0xFFFF0000u), sg[3]);
+            sg[4] = fmaf(ds, __uint_as_float(w2 << 16), sg[4]); sg[5] = fmaf(ds, __uint_as_float(w2 & 0xFFFF0000u), sg[5]);
+            sg[6] = fmaf(ds, __uint_as_float(w3 << 16), sg[6]); sg[7] = fmaf(ds, __uint_as_float(w3 & 0xFFFF0000u), sg[7]);
+            if (q32 == 0) sgb += ds;
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(b_empty + 8 * stage);
         if (++stage == ns) stage = 0;
       }
-      // combine the eight point-interleaved partial sums of every atom (lanes j8 = 0..7), then lane j8 adds column j8 of the atom
+      if (do_sig && t < 64) asm volatile("cp.async.wait_all;" ::: "memory");      // the two zero-filled look-ahead copies past u1
+      // combine the eight point-interleaved partial sums of the atom (lanes j8 = 0..7), then lane j8 adds column j8 of the atom
       if (do_bias || do_sig) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int k = 0; k < 8; ++k) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-              bs[h][k] += __shfl_xor_sync(0xffffffffu, bs[h][k], o);
-              sg[h][k] += __shfl_xor_sync(0xffffffffu, sg[h][k], o);
-            }
+          for (int o = 1; o < 8; o <<= 1) {
+            bs[k] += __shfl_xor_sync(0xffffffffu, bs[k], o);
+            sg[k] += __shfl_xor_sync(0xffffffffu, sg[k], o);
           }
         }
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) sgb += __shfl_xor_sync(0xffffffffu, sgb, o);
       }
       if (do_bias) {
+        float mine = 0.f;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int atom = q16 + 16 * h;
-          float mine = 0.f;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) if (k == j8) mine = bs[h][k];
-          const int col = atom * 8 + j8;
-          if (atom < a_atoms && col >= J.m_first && col < J.m_valid) atomicAdd(J.bias_out + col - J.m_first, mine);
-        }
+        for (int k = 0; k < 8; ++k) if (k == j8) mine = bs[k];
+        const int col = q32 * 8 + j8;
+        if (q32 < a_atoms && col >= J.m_first && col < J.m_valid) atomicAdd(J.bias_out + col - J.m_first, mine);
       }
       if (do_sig) {
+        float mine = 0.f;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float mine = 0.f;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) if (k == j8) mine = sg[h][k];
-          atomicAdd(J.sig_out + (q16 + 16 * h) * 8 + j8, mine);
-        }
+        for (int k = 0; k < 8; ++k) if (k == j8) mine = sg[k];
+        atomicAdd(J.sig_out + q32 * 8 + j8, mine);
         if (t == 0) atomicAdd(J.sig_bias, sgb);
       }
       // accumulators -> flat gradient
@@ -575,9 +570,11 @@ mlp_wgrad_kernel(const WgradParams p) {
       tc_fence_after();
       const int m_halves = J.m_blk >> 1;
       const bool vec4 = (J.ld & 3) == 0 && ((uintptr_t)J.out & 15) == 0 && (J.n_valid & 3) == 0;
+      const bool ones1 = J.bias_out != nullptr && J.bias_col >= 0 && J.bias_reg == 1;      // dY column sums = accumulator column bias_col
+      const bool ones2 = J.bias_out != nullptr && J.bias_col >= 0 && J.bias_reg == 2;
       for (int mh = 0; mh < m_halves; ++mh) {
         const int m = mh * 128 + (int)(q * 32u) + lane;          // output row (out-feature)
-        for (int c32 = 0; c32 < 2 * J.n_blk; ++c32) {
+        for (int c32 = (int)csel; c32 < 2 * J.n_blk; c32 += 2) {
           float v[32];
           tmem_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)mh * 256u + (uint32_t)c32 * 32u, v);
           tmem_ld_wait();
@@ -594,10 +591,16 @@ mlp_wgrad_kernel(const WgradParams p) {
               for (int jj = 0; jj < 32; ++jj)
                 if (c32 * 32 + jj < J.n_valid) atomicAdd(dst + jj, v[jj]);
             }
+            if (ones1 && (J.bias_col >> 5) == c32) {
+              float b = 0.f;
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) if (jj == (J.bias_col & 31)) b = v[jj];
+              atomicAdd(J.bias_out + m - J.m_first, b);
+            }
           }
         }
       }
-      for (int c32 = 0; c32 < 2 * J.n2_blk; ++c32) {            // second B operand (m_blk == 2): TMEM columns 256..
+      for (int c32 = (int)csel; c32 < 2 * J.n2_blk; c32 += 2) {            // second B operand (m_blk == 2): TMEM columns 256..
         const int m = (int)(q * 32u) + lane;
         float v[32];
         tmem_ld32(tmem_base + ((q * 32u) << 16) + 256u + (uint32_t)c32 * 32u, v);
@@ -607,6 +610,12 @@ mlp_wgrad_kernel(const WgradParams p) {
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj)
             if (c32 * 32 + jj < J.n2_valid) atomicAdd(dst + jj, v[jj]);
+          if (ones2 && (J.bias_col >> 5) == c32) {
+            float b = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) if (jj == (J.bias_col & 31)) b = v[jj];
+            atomicAdd(J.bias_out + m - J.m_first, b);
+          }
         }
       }
       tc_fence_before();
@@ -749,16 +758,20 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
       WgradJob& j = wp.job[nj];
       j.a = a; j.a_blobs = a_blobs; j.a_first = a_first; j.m_blk = m_blk; j.b = b; j.b_blobs = b_blobs; j.b_first = b_first;
       j.n_blk = n_blk; j.out = out; j.ld = ld; j.m_first = m_first; j.m_valid = m_valid; j.n_valid = n_valid; j.bias_out = bias;
+      j.bias_col = -1; j.bias_reg = 0;
       weight[nj] = m_blk + n_blk;       // HBM bytes per point ~ blobs loaded
       ++nj;
     };
     const uint8_t* dh[8];
     for (int i = 0; i < 8; ++i) dh[i] = w8 + W.off_dh[i];
     // trunk layers
+    // PE(x) blobs carry 1.0 in their pad column 63 (PE(viewdir): column 27), so db = dY^T 1 comes out of the same MMAs
     add(dh[0], 4, 0, 4, stash + S.off_embx, 1, 0, 1, grad + L.w[0], 63, 0, 256, 63, grad + L.b[0]);
+    wp.job[nj - 1].bias_col = 63; wp.job[nj - 1].bias_reg = 1;
     for (int l = 1; l < 8; ++l) {
       if (l == 5) {
         add(dh[5], 4, 0, 4, stash + S.off_embx, 1, 0, 1, grad + L.w[5], 319, 0, 256, 63, grad + L.b[5]);
+        wp.job[nj - 1].bias_col = 63; wp.job[nj - 1].bias_reg = 1;
         add(dh[5], 4, 0, 4, stash + S.off_h[4], 4, 0, 4, grad + L.w[5] + 63, 319, 0, 256, 256, nullptr);
       } else {
         add(dh[l], 4, 0, 4, stash + S.off_h[l - 1], 4, 0, 4, grad + L.w[l], 256, 0, 256, 256, grad + L.b[l]);
@@ -771,7 +784,7 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
     NB_CUDA(h, cudaMemsetAsync(fold_g, 0, kFoldFloats * sizeof(float), st));
     add(w8 + W.off_dg, 2, 0, 2, stash + S.off_h[7], 4, 0, 4, fold_g, 256, 0, 128, 256, fold_g + 128 * 256);
     { WgradJob& j = wp.job[nj - 1]; j.b2 = stash + S.off_embd; j.b2_blobs = 1; j.b2_first = 0; j.n2_blk = 1; j.n2_valid = 27;
-      j.out2 = grad + L.wd + 256; j.ld2 = 283; weight[nj - 1] += 1;
+      j.out2 = grad + L.wd + 256; j.ld2 = 283; weight[nj - 1] += 1; j.bias_col = 27; j.bias_reg = 2;
       j.sig_draw = d_raw; j.sig_out = grad + L.ws; j.sig_bias = grad + L.bs; }
     // rgb head: A = d_raw blob (cols 0..2 = d_rgb), stored twice so that M = 128 is addressable
     add(w8 + W.off_draw, 2, 0, 2, stash + S.off_g, 2, 0, 2, grad + L.wc, 128, 0, 3, 128, grad + L.bc);          // dWc, dbc
