@@ -311,47 +311,54 @@ struct WgradJob {
   int n_stages;          // ring stages for this job: min(kWgMaxStages, kWgRingBytes / stage bytes)
   long long work_begin;  // sum of weight * n_units over the preceding jobs
 };
-struct WgradParams { WgradJob job[kMaxJobs]; int n_jobs; long long n_tiles; long long n_points; long long total_work; int abl;
-                     unsigned long long* prof; };   // prof: optional [grid][4] ns time stamps (NB_TC_PROF diagnostic)
+struct WgradParams {
+  WgradJob job[kMaxJobs];
+  int n_jobs;
+  long long n_tiles, n_points, total_work;
+  int abl;
+  int chunk_units;             // units (64 points) per dynamically claimed chunk
+  unsigned int* counters;      // [kMaxJobs] next unclaimed chunk of every job (zeroed before the launch)
+  unsigned long long* prof;    // optional [grid][4] ns time stamps (NB_TC_PROF diagnostic)
+};
 
 constexpr int kWgThreads = 320;                         // warp0 producer, warp1 MMA, warps 2-9 column sums + accumulator flush
-// Operand ring: 224 KB cut into as many stages as fit the job's unit (4..8 half blobs of 8 KB = 64 points of every operand): 3 stages of
-// 64 KB for the trunk layers, 4 x 56 KB for the folded view layer, 5 x 40 KB for the two PE(x) jobs, 6 x 32 KB for the rgb head.  What
+// Operand ring: 216 KB cut into as many stages as fit the job's unit (4..8 half blobs of 8 KB = 64 points of every operand): 3 stages of
+// 64 KB for the trunk layers, 3 x 56 KB for the folded view layer, 5 x 40 KB for the two PE(x) jobs, 6 x 32 KB for the rgb head.  What
 // a CTA gets of the HBM stream follows the bytes it keeps in flight (measured: with 3 stages for every job the CTAs of the 32 / 40 KB
 // jobs took 1.29 ms for the same byte count the 64 KB jobs streamed in 0.96 ms, and the kernel ends with its slowest CTA), so every
-// job keeps ~200 KB in flight whatever its unit size.
+// job keeps 170-200 KB in flight whatever its unit size.
 constexpr int kWgMaxStages = 6;
-constexpr uint32_t kWgRingBytes = 224 * 1024;
+constexpr uint32_t kWgRingBytes = 216 * 1024;
 constexpr uint32_t kWgOffBar = kWgRingBytes;            // full[6] | empty[6] (+64) | done (+128) | tmem slot (+136) | free (+144)
-constexpr uint32_t kWgOffSig = kWgOffBar + 256;         // [kWgMaxStages][64] fp32 d_sigma of the stage's points
-constexpr uint32_t kWgSmemBytes = kWgOffSig + kWgMaxStages * 256 + 1024;
+constexpr uint32_t kWgOffMeta = kWgOffBar + 192;        // [kWgMaxStages] x 8 B: what the stage holds (written by the producer, see WgMeta)
+constexpr uint32_t kWgOffSig = kWgOffBar + 256;         // [3][64 rows x 16 B] d_raw rows of the stage's points (density-head rider, <= 3 stages)
+constexpr uint32_t kWgSigStages = 3;
+constexpr uint32_t kWgSmemBytes = kWgOffSig + kWgSigStages * 1024 + 1024;
 static_assert(kWgSmemBytes <= 232448, "wgrad ring exceeds the 227 KB of shared memory a CTA can have");
+// stage descriptor word 0: job | flags
+constexpr uint32_t kWgFirst = 1u << 8, kWgLast = 1u << 9, kWgEnd = 1u << 10;
 
-// One CTA's share of a job: the kernel's work is the concatenation over jobs of n_units units costing `weight` (operand
-// blobs per unit) each; CTA c owns the slice [total*c/G, total*(c+1)/G) of that line and a unit belongs to the CTA that
-// holds its first blob.  So every CTA streams the same number of bytes (+-1 unit) and at most n_jobs-1 CTAs straddle a job
-// boundary (they flush their accumulator and continue with the next job).
-__device__ __forceinline__ bool wg_segment(const WgradParams& p, int j, long long lo, long long hi, long long n_units, long long& u0,
-                                           long long& u1) {
-  const long long w = p.job[j].weight;
-  const long long a = lo - p.job[j].work_begin, b = hi - p.job[j].work_begin;
-  u0 = a <= 0 ? 0 : (a + w - 1) / w;
-  u1 = b <= 0 ? 0 : (b + w - 1) / w;
-  if (u0 > n_units) u0 = n_units;
-  if (u1 > n_units) u1 = n_units;
-  return u0 < u1;
+// Work distribution.  A job's units are claimed in chunks of `chunk_units` from a per-job atomic counter.  Every CTA starts on
+// its HOME job -- the one that holds the start of its share of the byte-weighted line of work, so jobs get CTAs in proportion to
+// their traffic -- and keeps claiming there; when the job is exhausted it flushes its accumulator and moves to the job with the
+// most unclaimed bytes left.  (A static equal-byte split finished between 0.92 and 1.15 ms per CTA on the fine pass: SMs differ
+// in what they get of the HBM stream, and the kernel ends with its slowest CTA.)  Only the producer thread talks to the counters;
+// it publishes what every stage holds (job, unit, first / last stage of a segment, end of work) in shared memory before arming
+// the stage's barrier, and the MMA / column-sum warps follow those descriptors.
+__device__ __forceinline__ int wg_home_job(const WgradParams& p, long long lo) {
+  int h = 0;
+  for (int j = 0; j < p.n_jobs; ++j) if (p.job[j].work_begin <= lo) h = j;
+  return h;
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 mlp_wgrad_kernel(const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t s_bar = sbase + kWgOffBar;
+  const uint32_t s_bar = sbase + kWgOffBar, s_meta = sbase + kWgOffMeta;
   const uint32_t b_full = s_bar, b_empty = s_bar + 64, b_done = s_bar + 128, s_tmem = s_bar + 136, b_free = s_bar + 144;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long n_units = p.n_tiles * 2;          // units of work: half tiles (64 points); unit u -> tile u>>1, half u&1
-  const long long lo = p.total_work * (long long)blockIdx.x / (long long)gridDim.x;
-  const long long hi = p.total_work * ((long long)blockIdx.x + 1) / (long long)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgMaxStages; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1 + 8); }
@@ -376,85 +383,116 @@ mlp_wgrad_kernel(const WgradParams p) {
       // number of stages in use changes from job to job.  Before the first load of a CTA's next job the ring is drained: the new
       // job's stage slots have another size and would overlap slots the MMAs may still be reading.
       uint32_t pmask = (1u << kWgMaxStages) - 1u;
-      bool first_seg = true;
-      for (int j = 0; j < p.n_jobs; ++j) {
-        long long u0, u1;
-        if (!wg_segment(p, j, lo, hi, n_units, u0, u1)) continue;
+      const long long C = p.chunk_units;
+      const long long n_chunks = (n_units + C - 1) / C;
+      int j = wg_home_job(p, p.total_work * (long long)blockIdx.x / (long long)gridDim.x);
+      bool any = false;
+      long long units_done = 0;
+      while (true) {
+        // ---- claim the first chunk of a segment: the home job first, afterwards whichever job has the most bytes unclaimed
+        long long c = (long long)atomicAdd(p.counters + j, 1u);
+        while (c >= n_chunks) {
+          long long best = 0; int bj = -1;
+          for (int k = 0; k < p.n_jobs; ++k) {
+            const long long taken = (long long)*reinterpret_cast<volatile unsigned int*>(p.counters + k);
+            const long long left = (n_chunks - taken) * p.job[k].weight;
+            if (left > best) { best = left; bj = k; }
+          }
+          if (bj < 0) break;
+          j = bj;
+          c = (long long)atomicAdd(p.counters + j, 1u);
+        }
+        if (c >= n_chunks) break;
         const WgradJob& J = p.job[j];
         const uint32_t stage_bytes = (uint32_t)(J.m_blk + J.n_blk + J.n2_blk) * 8192u;
         const uint32_t ns = (uint32_t)J.n_stages;
-        if (!first_seg)
+        if (any)
           for (int i = 0; i < kWgMaxStages; ++i) mbar_wait(b_empty + 8 * i, (pmask >> i) & 1u);
-        first_seg = false;
+        any = true;
         uint32_t stage = 0;
-        for (long long u = u0; u < u1; ++u) {
-          const long long tile = u >> 1;
-          const long long tile_a = (p.abl & 64) ? (tile & 63) : tile;      // experiments: operands from an L2-resident window
-          const long long tile_b = (p.abl & 128) ? (tile & 63) : tile;
-          const uint32_t half = (uint32_t)(u & 1) * 8192u;
-          mbar_wait(b_empty + 8 * stage, (pmask >> stage) & 1u);
-          pmask ^= 1u << stage;
-          mbar_expect_tx(b_full + 8 * stage, stage_bytes);
-          const uint32_t dst = sbase + stage * stage_bytes;
-          for (int k = 0; k < J.m_blk; ++k)
-            bulk_g2s(dst + (uint32_t)k * 8192u, J.a + ((size_t)tile_a * J.a_blobs + J.a_first + k) * kBlobBytes + half, 8192u, b_full + 8 * stage);
-          for (int k = 0; k < J.n_blk; ++k)
-            bulk_g2s(dst + (uint32_t)(J.m_blk + k) * 8192u, J.b + ((size_t)tile_b * J.b_blobs + J.b_first + k) * kBlobBytes + half, 8192u,
-                     b_full + 8 * stage);
-          for (int k = 0; k < J.n2_blk; ++k)
-            bulk_g2s(dst + (uint32_t)(J.m_blk + J.n_blk + k) * 8192u, J.b2 + ((size_t)tile_b * J.b2_blobs + J.b2_first + k) * kBlobBytes + half,
-                     8192u, b_full + 8 * stage);
-          if (++stage == ns) stage = 0;
+        bool first = true;
+        while (c < n_chunks) {
+          const long long cn = (long long)atomicAdd(p.counters + j, 1u);      // next chunk, claimed early: its latency hides behind this chunk
+          const long long ua = c * C, ub = (ua + C < n_units) ? ua + C : n_units;
+          for (long long u = ua; u < ub; ++u) {
+            const long long tile = u >> 1;
+            const long long tile_a = (p.abl & 64) ? (tile & 63) : tile;      // experiments: operands from an L2-resident window
+            const long long tile_b = (p.abl & 128) ? (tile & 63) : tile;
+            const uint32_t half = (uint32_t)(u & 1) * 8192u;
+            mbar_wait(b_empty + 8 * stage, (pmask >> stage) & 1u);
+            pmask ^= 1u << stage;
+            const uint32_t flags = (uint32_t)j | (first ? kWgFirst : 0u) | ((u == ub - 1 && cn >= n_chunks) ? kWgLast : 0u);
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(s_meta + 8u * stage), "r"(flags), "r"((uint32_t)u) : "memory");
+            first = false;
+            long long rows = J.sig_draw ? p.n_points - u * 64 : 0;           // density-head rider: the unit's d_raw rows ride along
+            rows = rows > 64 ? 64 : (rows < 0 ? 0 : rows);
+            mbar_expect_tx(b_full + 8 * stage, stage_bytes + (uint32_t)rows * 16u);
+            const uint32_t dst = sbase + stage * stage_bytes;
+            for (int k = 0; k < J.m_blk; ++k)
+              bulk_g2s(dst + (uint32_t)k * 8192u, J.a + ((size_t)tile_a * J.a_blobs + J.a_first + k) * kBlobBytes + half, 8192u, b_full + 8 * stage);
+            for (int k = 0; k < J.n_blk; ++k)
+              bulk_g2s(dst + (uint32_t)(J.m_blk + k) * 8192u, J.b + ((size_t)tile_b * J.b_blobs + J.b_first + k) * kBlobBytes + half, 8192u,
+                       b_full + 8 * stage);
+            for (int k = 0; k < J.n2_blk; ++k)
+              bulk_g2s(dst + (uint32_t)(J.m_blk + J.n_blk + k) * 8192u, J.b2 + ((size_t)tile_b * J.b2_blobs + J.b2_first + k) * kBlobBytes + half,
+                       8192u, b_full + 8 * stage);
+            if (rows > 0) bulk_g2s(sbase + kWgOffSig + stage * 1024u, J.sig_draw + u * 64 * 4, (uint32_t)rows * 16u, b_full + 8 * stage);
+            if (++stage == ns) stage = 0;
+            ++units_done;
+          }
+          c = cn;
         }
       }
+      // ---- end of work: an empty stage that only carries the flag (stage 0 of a drained ring)
+      if (any)
+        for (int i = 0; i < kWgMaxStages; ++i) mbar_wait(b_empty + 8 * i, (pmask >> i) & 1u);
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(s_meta), "r"(kWgEnd), "r"(0u) : "memory");
+      mbar_arrive(b_full);
       stamp(1);      // last load issued
+      if (p.prof) p.prof[(size_t)blockIdx.x * 4 + 2] = (unsigned long long)units_done;
     }
   } else if (warp == 1) {
-    uint32_t cmask = 0, seg = 0;
-    for (int j = 0; j < p.n_jobs; ++j) {
-      long long u0, u1;
-      if (!wg_segment(p, j, lo, hi, n_units, u0, u1)) continue;
-      const WgradJob& J = p.job[j];
+    uint32_t cmask = 0, seg = 0, stage = 0;
+    while (true) {
+      mbar_wait(b_full + 8 * stage, (cmask >> stage) & 1u);
+      cmask ^= 1u << stage;
+      uint32_t flags;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(flags) : "r"(s_meta + 8u * stage));
+      if (flags & kWgEnd) break;
+      const WgradJob& J = p.job[flags & 0xFFu];
       const uint32_t stage_bytes = (uint32_t)(J.m_blk + J.n_blk + J.n2_blk) * 8192u, ns = (uint32_t)J.n_stages;
-      uint32_t stage = 0;
-      const uint32_t idesc = umma_idesc(128, 64 * J.n_blk, 1, 1);      // both operands MN-major
-      const uint32_t idesc2 = umma_idesc(128, J.n2_blk > 0 ? 64 * J.n2_blk : 64, 1, 1);
-      const int m_halves = J.m_blk >> 1;
-      if (seg > 0) { mbar_wait(b_free, (seg - 1) & 1); tc_fence_after(); }    // previous segment's accumulator has been drained
-      for (long long u = u0; u < u1; ++u) {
-        mbar_wait(b_full + 8 * stage, (cmask >> stage) & 1u);
-        cmask ^= 1u << stage;
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = sbase + stage * stage_bytes;
-          const uint32_t b_addr = a_addr + (uint32_t)J.m_blk * 8192u;
-          const uint32_t first = (u == u0) ? 0u : 1u;
-          if (!(p.abl & 512)) {      // 512: timing experiment without the MMAs (stages are released at once)
+      if ((flags & kWgFirst) && seg > 0) mbar_wait(b_free, (seg - 1) & 1);      // the previous segment's accumulator has been drained
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc(128, 64 * J.n_blk, 1, 1);      // both operands MN-major
+        const uint32_t idesc2 = umma_idesc(128, J.n2_blk > 0 ? 64 * J.n2_blk : 64, 1, 1);
+        const int m_halves = J.m_blk >> 1;
+        const uint32_t a_addr = sbase + stage * stage_bytes;
+        const uint32_t b_addr = a_addr + (uint32_t)J.m_blk * 8192u;
+        const uint32_t acc = (flags & kWgFirst) ? 0u : 1u;
+        if (!(p.abl & 512)) {      // 512: timing experiment without the MMAs (stages are released at once)
           // operands: half blobs [feature/8][64 points][8 features] laid end to end => atoms of 8 features every 1024 B (SBO),
           // 8-point groups every 128 B (LBO), a K16 slice every 256 B; 128 output rows (one m_half) = 16 atoms = 16 KB further
           for (int mh = 0; mh < m_halves; ++mh) {
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16)      // 64 points per stage = 4 x K16
               umma_ss(tmem_base + (uint32_t)mh * 256u, umma_desc_mn_noswz(a_addr + (uint32_t)mh * 16384u + k16 * 256u, 128, 1024),
-                      umma_desc_mn_noswz(b_addr + k16 * 256u, 128, 1024), idesc, (first | (uint32_t)k16) ? 1u : 0u);
+                      umma_desc_mn_noswz(b_addr + k16 * 256u, 128, 1024), idesc, (acc | (uint32_t)k16) ? 1u : 0u);
           }
           if (J.n2_blk > 0) {
             const uint32_t b2_addr = b_addr + (uint32_t)J.n_blk * 8192u;
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16)
               umma_ss(tmem_base + 256u, umma_desc_mn_noswz(a_addr + k16 * 256u, 128, 1024), umma_desc_mn_noswz(b2_addr + k16 * 256u, 128, 1024),
-                      idesc2, (first | (uint32_t)k16) ? 1u : 0u);
+                      idesc2, (acc | (uint32_t)k16) ? 1u : 0u);
           }
-          }
-          umma_commit(b_empty + 8 * stage);
-          if (u == u1 - 1) umma_commit(b_done);
         }
-        __syncwarp();
-        if (++stage == ns) stage = 0;
+        umma_commit(b_empty + 8 * stage);
+        if (flags & kWgLast) umma_commit(b_done);
       }
-      ++seg;
+      __syncwarp();
+      if (flags & kWgLast) { ++seg; stage = 0; } else if (++stage == ns) stage = 0;
     }
-    if (lane == 0) stamp(2);      // last MMA issued
   } else {
     // ---- column sums (bias gradients, density-head rider) from the staged operands, then the TMEM -> global flush: EIGHT warps ----
     // (two per scheduler: with one warp per scheduler the dependent unpack / add chains ran at ~0.25 IPC and the jobs with the most
@@ -469,76 +507,58 @@ mlp_wgrad_kernel(const WgradParams p) {
     const int q32 = t >> 3;                   // 32 groups of 8 lanes: group g owns atom g
     const uint32_t q = (uint32_t)warp & 3u;   // TMEM lane quarter this warp may read
     const uint32_t csel = ((uint32_t)warp - 2u) >> 2;     // the two warps of a quarter take alternate 32-column chunks of the flush
-    uint32_t cmask = 0, seg = 0;
-    for (int j = 0; j < p.n_jobs; ++j) {
-      long long u0, u1;
-      if (!wg_segment(p, j, lo, hi, n_units, u0, u1)) continue;
-      const WgradJob& J = p.job[j];
+    uint32_t cmask = 0, seg = 0, stage = 0;
+    float bs[8], sg[8], sgb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { bs[k] = 0.f; sg[k] = 0.f; }
+    while (true) {
+      mbar_wait(b_full + 8 * stage, (cmask >> stage) & 1u);
+      cmask ^= 1u << stage;
+      uint32_t flags, u32;
+      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(flags), "=r"(u32) : "r"(s_meta + 8u * stage));
+      if (flags & kWgEnd) break;
+      const WgradJob& J = p.job[flags & 0xFFu];
       const uint32_t stage_bytes = (uint32_t)(J.m_blk + J.n_blk + J.n2_blk) * 8192u, ns = (uint32_t)J.n_stages;
-      uint32_t stage = 0;
       const int a_atoms = 8 * J.m_blk;                      // dY operand: 16 or 32 atoms
       const bool do_bias = J.bias_out != nullptr && J.bias_col < 0 && !(p.abl & 256);      // 256: timing experiment without the sums
       const bool do_sig = J.sig_draw != nullptr && !(p.abl & 256);       // rider on the B operand (N = 256 = 32 atoms)
-      float bs[8], sg[8], sgb = 0.f;
+      const uint32_t st_base = sbase + stage * stage_bytes;
+      if (do_bias && q32 < a_atoms) {
+        const uint32_t base = st_base + (uint32_t)q32 * 1024u + (uint32_t)j8 * 16u;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { bs[k] = 0.f; sg[k] = 0.f; }
-      // d_sigma of the stage's 64 points travels global -> shared by 4-byte cp.async, issued TWO units ahead into a ring of four
-      // 256-byte slots (under a saturated HBM stream a global load outlasts a stage, and a register prefetch would stall the warp at
-      // its first use); points past the end are zero-filled (src-size 0) and contribute nothing
-      auto issue_ds = [&](long long u) {
-        const long long pt = u * 64 + t;
-        const bool ok = u < u1 && pt < p.n_points;
-        const float* src = J.sig_draw + (ok ? pt * 4 + 3 : 3);
-        const uint32_t dst = sbase + kWgOffSig + (uint32_t)((u - u0) & 3) * 256u + (uint32_t)t * 4u;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4u : 0u) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      };
-      if (do_sig && t < 64) { issue_ds(u0); issue_ds(u0 + 1); }
-      for (long long u = u0; u < u1; ++u) {
-        const uint32_t sig = sbase + kWgOffSig + (uint32_t)((u - u0) & 3) * 256u;
-        if (do_sig) {
-          if (t < 64) {
-            issue_ds(u + 2);                                              // slot of unit u-2: every thread is past its reads (barrier of u-1)
-            asm volatile("cp.async.wait_group 2;" ::: "memory");          // this unit's values have landed
-          }
-          named_bar_sync(1, kWgThreads - 64);
+        for (uint32_t i = 0; i < 8; ++i) {
+          uint32_t w0, w1, w2, w3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + i * 128u));
+          bs[0] += __uint_as_float(w0 << 16); bs[1] += __uint_as_float(w0 & 0xFFFF0000u);
+          bs[2] += __uint_as_float(w1 << 16); bs[3] += __uint_as_float(w1 & 0xFFFF0000u);
+          bs[4] += __uint_as_float(w2 << 16); bs[5] += __uint_as_float(w2 & 0xFFFF0000u);
+          bs[6] += __uint_as_float(w3 << 16); bs[7] += __uint_as_float(w3 & 0xFFFF0000u);
         }
-        mbar_wait(b_full + 8 * stage, (cmask >> stage) & 1u);
-        cmask ^= 1u << stage;
-        const uint32_t st_base = sbase + stage * stage_bytes;
-        if (do_bias && q32 < a_atoms) {
-          const uint32_t base = st_base + (uint32_t)q32 * 1024u + (uint32_t)j8 * 16u;
-#pragma unroll
-          for (uint32_t i = 0; i < 8; ++i) {
-            uint32_t w0, w1, w2, w3;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + i * 128u));
-            bs[0] += __uint_as_float(w0 << 16); bs[1] += __uint_as_float(w0 & 0xFFFF0000u);
-            bs[2] += __uint_as_float(w1 << 16); bs[3] += __uint_as_float(w1 & 0xFFFF0000u);
-            bs[4] += __uint_as_float(w2 << 16); bs[5] += __uint_as_float(w2 & 0xFFFF0000u);
-            bs[6] += __uint_as_float(w3 << 16); bs[7] += __uint_as_float(w3 & 0xFFFF0000u);
-          }
-        }
-        if (do_sig) {
-          const uint32_t base = st_base + (uint32_t)(a_atoms + q32) * 1024u + (uint32_t)j8 * 16u;
-#pragma unroll
-          for (uint32_t i = 0; i < 8; ++i) {
-            uint32_t w0, w1, w2, w3;
-            float ds;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + i * 128u));
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ds) : "r"(sig + ((uint32_t)j8 + 8u * i) * 4u));
-            sg[0] = fmaf(ds, __uint_as_float(w0 << 16), sg[0]); sg[1] = fmaf(ds, __uint_as_float(w0 & 0xFFFF0000u), sg[1]);
-            sg[2] = fmaf(ds, __uint_as_float(w1 << 16), sg[2]); sg[3] = fmaf(ds, __uint_as_float(w1 & 0xFFFF0000u), sg[3]);
-            sg[4] = fmaf(ds, __uint_as_float(w2 << 16), sg[4]); sg[5] = fmaf(ds, __uint_as_float(w2 & 0xFFFF0000u), sg[5]);
-            sg[6] = fmaf(ds, __uint_as_float(w3 << 16), sg[6]); sg[7] = fmaf(ds, __uint_as_float(w3 & 0xFFFF0000u), sg[7]);
-            if (q32 == 0) sgb += ds;
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(b_empty + 8 * stage);
-        if (++stage == ns) stage = 0;
       }
-      if (do_sig && t < 64) asm volatile("cp.async.wait_all;" ::: "memory");      // the two zero-filled look-ahead copies past u1
-      // combine the eight point-interleaved partial sums of the atom (lanes j8 = 0..7), then lane j8 adds column j8 of the atom
+      if (do_sig) {
+        // d_sigma of point r of the stage = float 3 of staged d_raw row r; rows past the last point were not copied and count as zero
+        const uint32_t base = st_base + (uint32_t)(a_atoms + q32) * 1024u + (uint32_t)j8 * 16u;
+        const uint32_t sig = sbase + kWgOffSig + stage * 1024u;
+        const long long left = p.n_points - (long long)u32 * 64;
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) {
+          uint32_t w0, w1, w2, w3;
+          float ds;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + i * 128u));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ds) : "r"(sig + ((uint32_t)j8 + 8u * i) * 16u + 12u));
+          if ((long long)(j8 + 8 * (int)i) >= left) ds = 0.f;
+          sg[0] = fmaf(ds, __uint_as_float(w0 << 16), sg[0]); sg[1] = fmaf(ds, __uint_as_float(w0 & 0xFFFF0000u), sg[1]);
+          sg[2] = fmaf(ds, __uint_as_float(w1 << 16), sg[2]); sg[3] = fmaf(ds, __uint_as_float(w1 & 0xFFFF0000u), sg[3]);
+          sg[4] = fmaf(ds, __uint_as_float(w2 << 16), sg[4]); sg[5] = fmaf(ds, __uint_as_float(w2 & 0xFFFF0000u), sg[5]);
+          sg[6] = fmaf(ds, __uint_as_float(w3 << 16), sg[6]); sg[7] = fmaf(ds, __uint_as_float(w3 & 0xFFFF0000u), sg[7]);
+          if (q32 == 0) sgb += ds;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_empty + 8 * stage);
+      if (!(flags & kWgLast)) { if (++stage == ns) stage = 0; continue; }
+      stage = 0;
+      // ---- last stage of a segment: combine the eight point-interleaved partial sums of the atom (lanes j8 = 0..7); lane j8 adds column j8
       if (do_bias || do_sig) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -565,6 +585,9 @@ mlp_wgrad_kernel(const WgradParams p) {
         atomicAdd(J.sig_out + q32 * 8 + j8, mine);
         if (t == 0) atomicAdd(J.sig_bias, sgb);
       }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { bs[k] = 0.f; sg[k] = 0.f; }
+      sgb = 0.f;
       // accumulators -> flat gradient
       mbar_wait(b_done, seg & 1);
       tc_fence_after();
@@ -674,7 +697,7 @@ fold_grads_kernel(const float* __restrict__ prm, NbParamLayout L, const float* _
 // host side
 // ------------------------------------------------------------------------------------------
 size_t nb_tc_bwd_packed_bytes() { return bwd_w_off(kBwdSteps); }
-size_t nb_tc_bwd_ws_bytes(const nb_mlp_desc&, long long P) { return bwd_ws_layout(P).total + kFoldFloats * sizeof(float) + 256; }
+size_t nb_tc_bwd_ws_bytes(const nb_mlp_desc&, long long P) { return bwd_ws_layout(P).total + kFoldFloats * sizeof(float) + 256; }   // 256 >= chunk counters
 
 void nb_tc_bwd_add_blobs(const NbParamLayout& L, const std::function<void(size_t, int, int, int, int, int, int, int, int)>& add) {
   // blob[n][k] = W[k0+k][n0+n]  (B = W^T, rows = in-features, K = out-features)
@@ -692,8 +715,8 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
                    cudaStream_t st, int stages) {
   const NbParamLayout L = nb_param_layout(*d);
   const BwdWs W = bwd_ws_layout(P);
-  if (!ws || ws_bytes < W.total + kFoldFloats * sizeof(float)) {
-    NB_SET_ERR(h, "mlp bf16 backward: workspace %zu < %zu bytes", ws_bytes, W.total + kFoldFloats * sizeof(float));
+  if (!ws || ws_bytes < W.total + kFoldFloats * sizeof(float) + 256) {
+    NB_SET_ERR(h, "mlp bf16 backward: workspace %zu < %zu bytes", ws_bytes, W.total + kFoldFloats * sizeof(float) + 256);
     return NB_ERR_WORKSPACE;
   }
   NB_REQUIRE(h, ((uintptr_t)d_raw & 15) == 0 && ((uintptr_t)ws & 15) == 0 && ((uintptr_t)act_save & 15) == 0,
@@ -781,7 +804,7 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
     // gradients of Wf, b_feat and Wd[:, :256] (fold_grads_kernel below); its PE block is dWd[:, 256:283] directly.  The density head
     // (dW_sigma = d_sigma^T h7, db_sigma) rides on the h7 operand.  dg is read once, h7 once: 7 blobs where the unfolded layers took 15.
     float* fold_g = reinterpret_cast<float*>((uint8_t*)ws + W.total);              // [128][256] G  +  [128] column sums of dg
-    NB_CUDA(h, cudaMemsetAsync(fold_g, 0, kFoldFloats * sizeof(float), st));
+    NB_CUDA(h, cudaMemsetAsync(fold_g, 0, kFoldFloats * sizeof(float) + kMaxJobs * sizeof(unsigned int), st));   // + the chunk counters
     add(w8 + W.off_dg, 2, 0, 2, stash + S.off_h[7], 4, 0, 4, fold_g, 256, 0, 128, 256, fold_g + 128 * 256);
     { WgradJob& j = wp.job[nj - 1]; j.b2 = stash + S.off_embd; j.b2_blobs = 1; j.b2_first = 0; j.n2_blk = 1; j.n2_valid = 27;
       j.out2 = grad + L.wd + 256; j.ld2 = 283; weight[nj - 1] += 1; j.bias_col = 27; j.bias_reg = 2;
@@ -794,10 +817,17 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
     long long work = 0;
     for (int j = 0; j < nj; ++j) {
       wp.job[j].weight = weight[j]; wp.job[j].work_begin = work; work += (long long)weight[j] * n_tiles * 2;
-      const int fit = (int)(kWgRingBytes / ((uint32_t)weight[j] * 8192u));
+      int fit = (int)(kWgRingBytes / ((uint32_t)weight[j] * 8192u));
+      if (wp.job[j].sig_draw && fit > (int)kWgSigStages) fit = (int)kWgSigStages;
       wp.job[j].n_stages = fit > kWgMaxStages ? kWgMaxStages : fit;
     }
     wp.total_work = work;
+    // chunks of 16 units (1024 points) when every CTA gets >= 32 of them per job visit, else 8 / 4 / 1
+    {
+      const long long per_cta = n_tiles * 2 * nj / (h->sm_count > 0 ? h->sm_count : 1);
+      wp.chunk_units = per_cta >= 512 ? 16 : (per_cta >= 128 ? 8 : (per_cta >= 16 ? 4 : 1));
+    }
+    wp.counters = reinterpret_cast<unsigned int*>(fold_g + kFoldFloats);          // zeroed with the fold scratch above
     int begin = h->sm_count;
     if ((long long)begin > n_tiles * 2) begin = (int)(n_tiles * 2);
     static unsigned long long* prof_dev = nullptr;
@@ -815,16 +845,14 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
       cudaMemcpy(host, prof_dev, sizeof(host), cudaMemcpyDeviceToHost);
       unsigned long long t0 = ~0ull;
       for (int b = 0; b < begin; ++b) if (host[b * 4] < t0) t0 = host[b * 4];
-      fprintf(stderr, "nb_tc wgrad prof P=%lld grid=%d (cta: first job, last job | start, last load issued, last MMA issued, flushed [us])\n", (long long)P, begin);
+      fprintf(stderr, "nb_tc wgrad prof P=%lld grid=%d chunk=%d units (cta: home job, units done | start, end of loads, flushed [us])\n", (long long)P, begin,
+              wp.chunk_units);
       for (int b = 0; b < begin; ++b) {
-        const long long lo = work * b / begin, hi = work * (b + 1) / begin;
-        int j0 = -1, j1 = -1;
-        for (int j = 0; j < nj; ++j) {
-          const long long jb = wp.job[j].work_begin, je = jb + (long long)wp.job[j].weight * n_tiles * 2;
-          if (lo < je && hi > jb) { if (j0 < 0) j0 = j; j1 = j; }
-        }
-        fprintf(stderr, "  cta %3d: jobs %2d..%2d | %7.1f %7.1f %7.1f %7.1f\n", b, j0, j1, (host[b * 4] - t0) * 1e-3, (host[b * 4 + 1] - t0) * 1e-3,
-                (host[b * 4 + 2] - t0) * 1e-3, (host[b * 4 + 3] - t0) * 1e-3);
+        const long long lo = work * b / begin;
+        int j0 = 0;
+        for (int j = 0; j < nj; ++j) if (wp.job[j].work_begin <= lo) j0 = j;
+        fprintf(stderr, "  cta %3d: jobs %2d..%2d | %7.1f %7.1f %7.1f %7.1f\n", b, j0, j0, (host[b * 4] - t0) * 1e-3, (host[b * 4 + 1] - t0) * 1e-3,
+                (double)host[b * 4 + 2], (host[b * 4 + 3] - t0) * 1e-3);
       }
     }
     fold_grads_kernel<<<256 + 128 + 1, 256, 0, st>>>(params, L, fold_g, grad);
