@@ -242,7 +242,7 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
   const uint32_t b_wfull = s_bar, b_wempty = s_bar + 32, b_pfull = s_bar + 64, b_aready = s_bar + 96, b_accready = s_bar + 112,
                  s_tmem = s_bar + 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t NSTAGE = CTA2 ? 4u : 2u;
+  constexpr uint32_t NSTAGE = CTA2 ? 4u : 2u;    // weight ring: 2 stages of one K block (two 32-k sub-blobs, 32 KB at N = 256)
   constexpr uint32_t STAGE_BYTES = CTA2 ? 16384u : 32768u;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = MC || rank == 0;      // MC: every CTA issues its own MMAs
@@ -344,20 +344,16 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
                 const int src = fwd_a_src(s, kb);
                 const uint32_t a_addr = (src < 0) ? (s_aux + slot * kBlobBytes) : (s_act + slot * kActBytes + (uint32_t)src * kBlobBytes);
                 const uint32_t b_addr = s_w + stage * STAGE_BYTES;
+                const uint32_t sub = fwd_blob_bytes(s) >> 1;      // the K block = two 32-k sub-blobs (SWIZZLE_64B images) laid end to end
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
-                  const uint64_t ad = umma_desc(a_addr + k4 * 32u, 16, 1024), bd = umma_desc(b_addr + k4 * 32u, 16, 1024);
-                  if (CTA2) umma_ss_2cta(d_tmem, ad, bd, idesc, (kb | k4) ? 1u : 0u);
-                  else umma_ss(d_tmem, ad, bd, idesc, (kb | k4) ? 1u : 0u);
+                  const uint64_t ad = umma_desc(a_addr + k4 * 32u, 16, 1024);
+                  const uint64_t bd = umma_desc_sw64(b_addr + (uint32_t)(k4 >> 1) * sub + (uint32_t)(k4 & 1) * 32u, 16, 512);
+                  umma_ss(d_tmem, ad, bd, idesc, (kb | k4) ? 1u : 0u);
                 }
-                if (CTA2) {
-                  umma_commit_2cta(b_wempty + 8 * stage);
-                  if (kb == nkb - 1) umma_commit_2cta(b_accready + 8 * slot);
-                } else {
-                  if (MC) umma_commit_mcast(b_wempty + 8 * stage);        // both CTAs' producers learn that I am done with it
-                  else umma_commit(b_wempty + 8 * stage);                 // stage is free once these MMAs retire
-                  if (kb == nkb - 1) umma_commit(b_accready + 8 * slot);  // accumulator complete
-                }
+                if (MC) umma_commit_mcast(b_wempty + 8 * stage);        // both CTAs' producers learn that I am done with it
+                else umma_commit(b_wempty + 8 * stage);                 // stage is free once these MMAs retire
+                if (kb == nkb - 1) umma_commit(b_accready + 8 * slot);  // accumulator complete
               }
               __syncwarp();
               if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -547,7 +543,7 @@ pack_kernel(const PackParams pp, const float* __restrict__ prm, uint8_t* __restr
       v[j] = x;
     }
     uint4 w = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-    *reinterpret_cast<uint4*>(out + d.dst_off + sw128_chunk((uint32_t)n, (uint32_t)c)) = w;
+    *reinterpret_cast<uint4*>(out + d.dst_off + wblob_chunk((uint32_t)d.n_rows, (uint32_t)n, (uint32_t)c)) = w;
   }
 }
 
@@ -647,6 +643,7 @@ static int launch_fwd(nb_handle_t h, FwdParams& fp, bool train, cudaStream_t st)
   static int mode_env = -1;
   if (mode_env < 0) { const char* e = getenv("NB_TC_CLUSTER"); mode_env = e ? atoi(e) : 2; }
   const int mode = mode_env;
+  if (mode == 1) { NB_SET_ERR(h, "NB_TC_CLUSTER=1 (cta_group::2 MMAs) is not available with the sub-blob weight ring"); return NB_ERR_UNSUPPORTED; }
   const bool cta2 = mode != 0;      // launched as clusters of 2
   if (mode == 1) {
     static_assert(sizeof(CUtensorMap) <= sizeof(h->w_tmap), "tensor map does not fit the handle slot");
@@ -703,7 +700,13 @@ static int launch_fwd(nb_handle_t h, FwdParams& fp, bool train, cudaStream_t st)
     cudaStreamSynchronize(st);
     cudaMemcpy(host, prof_dev, sizeof(host), cudaMemcpyDeviceToHost);
     double a[8] = {0}; int n = 0;
-    for (unsigned b = 0; b < cfg.gridDim.x; ++b) if (host[b * 8 + 3] > 0) { ++n; for (int k = 0; k < 8; ++k) a[k] += (double)host[b * 8 + k]; }
+    long long tmin = 1ll << 62, tmax = 0;
+    for (unsigned b = 0; b < cfg.gridDim.x; ++b) if (host[b * 8 + 3] > 0) {
+      ++n; for (int k = 0; k < 8; ++k) a[k] += (double)host[b * 8 + k];
+      if (host[b * 8 + 3] < tmin) tmin = host[b * 8 + 3];
+      if (host[b * 8 + 3] > tmax) tmax = host[b * 8 + 3];
+    }
+    fprintf(stderr, "nb_tc prof: MMA loop cycles per CTA min %lld max %lld (static round-robin tiles: the kernel ends with the slowest)\n", tmin, tmax);
     fprintf(stderr, "nb_tc prof P=%lld train=%d cta2=%d: mma_wait_aready=%.0f mma_wait_wfull=%.0f mma_wait_peerfull=%.0f mma_total=%.0f "
             "epi_wait_acc=%.0f epi_body=%.0f epi_prologue=%.0f\n",
             fp.P, (int)train, (int)cta2, a[0] / n, a[1] / n, a[2] / n, a[3] / n, a[4] / n, a[5] / n, a[6] / n);

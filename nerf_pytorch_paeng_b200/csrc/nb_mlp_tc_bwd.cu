@@ -56,9 +56,10 @@ BwdWs bwd_ws_layout(long long P) {
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kActBytes = 4 * kBlobBytes;
 constexpr uint32_t kOffAct = 0;
-constexpr uint32_t kOffAux = 2 * kActBytes;
-constexpr uint32_t kOffW = kOffAux + 2 * kBlobBytes;
-constexpr uint32_t kOffBar = kOffW + 2 * 32768;
+constexpr uint32_t kDgStages = 3;                 // W^T ring: 3 stages of one K block (two 32-k sub-blobs, 32 KB); the chain needs no aux tile, so the
+constexpr uint32_t kDgStageBytes = 32768;         // ring gets that space (a third stage: the forward's two leave its MMA warp waiting 14-21 % of the time)
+constexpr uint32_t kOffW = 2 * kActBytes;
+constexpr uint32_t kOffBar = kOffW + kDgStages * kDgStageBytes;
 constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;
 constexpr int kThreads = 576;      // warp 0 producer, warp 1 MMA, 8 epilogue warps per slot (two per TMEM lane quarter: column halves)
 constexpr int kEpi = 256;
@@ -87,7 +88,7 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_act = sbase + kOffAct, s_w = sbase + kOffW, s_bar = sbase + kOffBar;
-  const uint32_t b_wfull = s_bar, b_wempty = s_bar + 16, b_aready = s_bar + 32, b_accready = s_bar + 48, s_tmem = s_bar + 64;
+  const uint32_t b_wfull = s_bar, b_wempty = s_bar + 64, b_aready = s_bar + 128, b_accready = s_bar + 144, s_tmem = s_bar + 160;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long n_tiles = (p.P + 127) / 128;
   const uint32_t rank = MC ? cluster_ctarank() : 0u;
@@ -98,9 +99,11 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
   const long long max_it = (n_units + 2 * ncl - 1) / (2 * ncl);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (uint32_t i = 0; i < kDgStages; ++i) {
       mbar_init(b_wfull + 8 * i, 1);
       mbar_init(b_wempty + 8 * i, MC ? 2 : 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(b_aready + 8 * i, kEpi);
       mbar_init(b_accready + 8 * i, 1);
     }
@@ -115,7 +118,7 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
 
   if (warp == 0) {
-    // ---- W^T producer: 2 x 32 KB ring, ping-pong order (slot 0's whole step, then slot 1's)
+    // ---- W^T producer: 3 x 32 KB ring, ping-pong order (slot 0's whole step, then slot 1's)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (long long it = 0; it < max_it; ++it) {
@@ -126,18 +129,18 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
             if (unit_of(slot, it) >= n_units) continue;
             for (int kb = 0; kb < bwd_nkb(b); ++kb) {
               mbar_wait(b_wempty + 8 * stage, phase ^ 1);
-              mbar_expect_tx(b_wfull + 8 * stage, 32768u);
+              mbar_expect_tx(b_wfull + 8 * stage, kDgStageBytes);
+              const uint8_t* g = src + (size_t)kb * kDgStageBytes;
               if (MC) {     // my half of the stage, multicast into both CTAs' rings
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
-                  bulk_g2s_mcast(s_w + stage * 32768u + rank * 16384u + i * 8192u, src + (size_t)kb * 32768u + rank * 16384u + i * 8192u,
-                                 8192u, b_wfull + 8 * stage, (uint16_t)3);
+                  bulk_g2s_mcast(s_w + stage * kDgStageBytes + rank * 16384u + i * 8192u, g + rank * 16384u + i * 8192u, 8192u,
+                                 b_wfull + 8 * stage, (uint16_t)3);
               } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  bulk_g2s(s_w + stage * 32768u + i * 8192u, src + (size_t)kb * 32768u + i * 8192u, 8192u, b_wfull + 8 * stage);
+                for (int i = 0; i < 4; ++i) bulk_g2s(s_w + stage * kDgStageBytes + i * 8192u, g + i * 8192u, 8192u, b_wfull + 8 * stage);
               }
-              stage ^= 1; if (stage == 0) phase ^= 1;
+              if (++stage == kDgStages) { stage = 0; phase ^= 1; }
             }
           }
         }
@@ -160,16 +163,16 @@ mlp_dgrad_chain_kernel(const DgradParams p) {
             tc_fence_after();
             if (lane == 0) {
               const uint32_t a_addr = s_act + slot * kActBytes + (uint32_t)kb * kBlobBytes;
-              const uint32_t b_addr = s_w + stage * 32768u;
+              const uint32_t b_addr = s_w + stage * kDgStageBytes;
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)
-                umma_ss(d_tmem, umma_desc(a_addr + k4 * 32u, 16, 1024), umma_desc(b_addr + k4 * 32u, 16, 1024), idesc,
-                        (kb | k4) ? 1u : 0u);
+              for (int k4 = 0; k4 < 4; ++k4)      // the K block = two 32-k sub-blobs (SWIZZLE_64B images) laid end to end
+                umma_ss(d_tmem, umma_desc(a_addr + k4 * 32u, 16, 1024),
+                        umma_desc_sw64(b_addr + (uint32_t)(k4 >> 1) * 16384u + (uint32_t)(k4 & 1) * 32u, 16, 512), idesc, (kb | k4) ? 1u : 0u);
               if (MC) umma_commit_mcast(b_wempty + 8 * stage); else umma_commit(b_wempty + 8 * stage);
               if (kb == nkb - 1) umma_commit(b_accready + 8 * slot);
             }
             __syncwarp();
-            stage ^= 1; if (stage == 0) phase ^= 1;
+            if (++stage == kDgStages) { stage = 0; phase ^= 1; }
           }
         }
       }

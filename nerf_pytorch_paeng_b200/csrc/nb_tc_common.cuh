@@ -149,6 +149,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
 }
+// K-major operand with SWIZZLE_64B: rows (M/N index) are 64 B = 32 bf16 of K; 8-row groups every SBO = 512 B; layout_type = 4.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (4ull << 61);
+}
 // SWIZZLE_NONE ("interleave") MN-major operand: 16-byte atoms (8 bf16 of M/N) of 8 consecutive K rows are contiguous (128 B core
 // matrix); for this layout type the descriptor's SBO is the byte stride between atoms along M/N and LBO the stride between 8-row
 // groups along K (CUTLASS mma_traits_sm100.hpp, make_umma_desc<Major::MN>: ((1,n),(8,k)):((X,SBO),(1,LBO)) in uint128 units).
@@ -219,6 +224,13 @@ __device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float 
       : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
 }
 __host__ __device__ __forceinline__ uint32_t sw128_chunk(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
+// Packed WEIGHT blob of one 64-wide K block ([n_rows][64 k] bf16): two consecutive sub-blobs of 32 k each, every one the exact
+// SWIZZLE_64B shared-memory image of a [n_rows][32 k] K-major operand (rows of 64 B, 16-byte chunk c4 of row n stored at
+// c4 ^ ((n >> 1) & 3)).  One sub-blob = one stage of the weight ring (16 KB at 256 rows): twice as many, half as large stages as a
+// ring of whole blobs, so a stage is handed back after two MMAs and the refill latency has three stages to hide behind.
+__host__ __device__ __forceinline__ uint32_t wblob_chunk(uint32_t n_rows, uint32_t n, uint32_t c) {
+  return (c >> 2) * (n_rows * 64u) + n * 64u + (((c & 3u) ^ ((n >> 1) & 3u)) << 4);
+}
 // Stash / dY blob layout in HBM (16 KB = 128 points x 64 features bf16): [half = point/64][chunk = feature/8][point%64][16 B].
 // A warp whose lanes are 32 consecutive points writes 512 contiguous bytes per chunk straight from registers, and a half blob
 // (8 KB, contiguous) is a SWIZZLE_NONE MN-major UMMA operand for the weight-gradient GEMMs: atoms of 8 features every 1024 B (SBO),
