@@ -500,13 +500,21 @@ fold_feat_kernel(const float* __restrict__ prm, NbParamLayout L, float* __restri
   __shared__ float wd[256];
   wd[k] = prm[L.wd + (size_t)n * 283 + k];
   __syncthreads();
-  float acc = 0.f, accb = 0.f;
-#pragma unroll 8
-  for (int j = 0; j < 256; ++j) acc = fmaf(wd[j], prm[L.wf + (size_t)j * 256 + k], acc);
-  fold[(size_t)n * 256 + k] = acc;
-  if (k == 0) {
-    for (int j = 0; j < 256; ++j) accb = fmaf(wd[j], prm[L.bf + j], accb);
-    fold[128 * 256 + n] = accb + prm[L.bd + n];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four independent chains: the loop is latency-bound otherwise
+#pragma unroll 16
+  for (int j = 0; j < 256; j += 4) {
+    a0 = fmaf(wd[j], prm[L.wf + (size_t)j * 256 + k], a0);
+    a1 = fmaf(wd[j + 1], prm[L.wf + (size_t)(j + 1) * 256 + k], a1);
+    a2 = fmaf(wd[j + 2], prm[L.wf + (size_t)(j + 2) * 256 + k], a2);
+    a3 = fmaf(wd[j + 3], prm[L.wf + (size_t)(j + 3) * 256 + k], a3);
+  }
+  fold[(size_t)n * 256 + k] = (a0 + a1) + (a2 + a3);
+  if (k < 32) {                                       // b'[n]: one warp, shuffle-reduced
+    float b = 0.f;
+    for (int j = k; j < 256; j += 32) b = fmaf(wd[j], prm[L.bf + j], b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+    if (k == 0) fold[128 * 256 + n] = b + prm[L.bd + n];
   }
 }
 
