@@ -17,8 +17,6 @@ struct nb_handle_s {
   // per-device lazily initialised state (function attributes are per device; a process may hold one handle per GPU)
   bool fwd_attr_done[9];
   bool bwd_attr_done;
-  alignas(64) unsigned char w_tmap[128];   // CUtensorMap of the packed forward weights (pair mode), valid for w_tmap_for
-  const void* w_tmap_for;
 };
 
 #define NB_SET_ERR(h, ...) do { if (h) snprintf((h)->err, sizeof((h)->err), __VA_ARGS__); } while (0)

@@ -5,9 +5,12 @@
 //
 // One persistent CTA per SM (launched as clusters of two that share the weight stream), 576 threads, two 128-point tiles
 // ("slots") in flight:
-//   warp 0      weight producer: streams the pre-swizzled bf16 weight blobs (32 KB = 256 out-features x 64 in-features) from L2
-//               into a 2-stage shared-memory ring with cp.async.bulk (TMA unit) + mbarrier; in the default cluster mode each CTA
-//               fetches half of every stage and multicasts it into both CTAs' rings.
+//   warp 0      weight producer: streams the pre-swizzled bf16 weight blobs (32 KB = 256 out-features x 64 in-features, stored as two
+//               SWIZZLE_64B images of 32 in-features each, wblob_chunk() in nb_tc_common.cuh) from L2 into a 2-stage shared-memory
+//               ring with cp.async.bulk (TMA unit) + mbarrier; in the default cluster mode each CTA fetches half of every stage
+//               and multicasts it into both CTAs' rings.  (Ring stages of ONE sub-blob, 4 x 16 KB, were measured: the single
+//               issuing thread then pays its wait / fence / commit sequence per two MMAs instead of four and becomes the bound --
+//               inference 0.80 -> 1.09 ms.)
 //   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16) with A = the slot's activation tile in shared
 //               memory (K-major, 128B swizzle), B = the weight stage, D = the slot's 256 fp32 TMEM columns; tcgen05.commit
 //               releases the weight stage / signals the epilogue.
@@ -31,7 +34,6 @@
 // stores, no shared-memory read-back, no extra barrier.  The backward kernels (nb_mlp_tc_bwd.cu) consume those blobs directly as
 // MN-major UMMA operands.
 #include <stdlib.h>
-#include <cuda.h>
 #include "nb_mlp.h"
 #include "nb_tc_common.cuh"
 #include "nb_mlp_tc.h"
@@ -75,7 +77,6 @@ __constant__ TcSmall c_fw[kConstBanks];   // small fp32 parameters of the networ
 NbConstBankTable g_fw_banks;   // named barrier ids of the two epilogue groups
 
 struct FwdParams {
-  CUtensorMap tmap_w;     // pair mode only: packed forward blobs viewed as [rows, 64] bf16, box = 64 rows (8 KB), no swizzle (pre-swizzled images)
   const float* rays;      // [N,6]
   const float* z;         // [N,S]
   const float* x_emb;     // optional materialised embedding [P, ld_x] (forward_emb entry) or nullptr
@@ -221,20 +222,14 @@ __device__ __forceinline__ void epi_chunks(const FwdParams& p, int s, int c_begi
     asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(mdst), "r"(mw.x), "r"(mw.y), "r"(mw.z), "r"(mw.w) : "memory");
 }
 
-// CTA2 = true: the kernel runs as thread-block clusters of two CTAs on one TPC and every GEMM is a
-// tcgen05.mma.cta_group::2 with M = 256: CTA 0 (leader) owns rows 0..127, CTA 1 rows 128..255, each keeps its own
-// activation tiles / TMEM accumulators, and each streams only ITS HALF of every weight blob (N/2 rows), halving the
-// L2->SM weight stream per tile and doubling the depth of the weight ring (4 x 16 KB).  Only the leader issues MMAs;
-// the peer's MMA warp forwards "my half of stage k has landed" to the leader; tcgen05.commit multicasts the
-// stage-free / accumulator-ready arrivals to both CTAs; epilogue threads of the peer arrive on the leader's
-// a_ready barrier through DSMEM (mapa + mbarrier.arrive.release.cluster).
-// MC = true (exclusive with CTA2): clusters of two independent CTAs (each issues its own cta_group::1 MMAs) that SHARE
-// the weight stream: each CTA fetches half of every 32 KB weight stage and multicasts it into both CTAs' rings, halving
-// the L2->SM weight traffic; a stage is refilled once BOTH CTAs have retired its MMAs (commit multicast, count 2).
-template <bool TRAIN, bool DBG, bool CTA2, bool MC>
+// MC = true: clusters of two independent CTAs (each issues its own cta_group::1 MMAs) that SHARE the weight stream: each CTA fetches
+// half of every 32 KB weight stage and multicasts it into both CTAs' rings, halving the L2->SM weight traffic; a stage is refilled
+// once BOTH CTAs have retired its MMAs (commit multicast, count 2).  (A cta_group::2 variant -- M = 256 MMAs over the pair, each CTA
+// holding half of B -- was built in round 1, measured slower than this ring and retired.)
+template <bool TRAIN, bool DBG, bool MC>
 __global__ void __launch_bounds__(kThreads, 1)
-mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
-  constexpr bool PAIR = CTA2 || MC;
+mlp_fwd_chain_kernel(const FwdParams p) {
+  constexpr bool PAIR = MC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_act = sbase + kOffAct, s_aux = sbase + kOffAux, s_w = sbase + kOffW, s_bar = sbase + kOffBar;
@@ -242,13 +237,12 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
   const uint32_t b_wfull = s_bar, b_wempty = s_bar + 32, b_pfull = s_bar + 64, b_aready = s_bar + 96, b_accready = s_bar + 112,
                  s_tmem = s_bar + 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t NSTAGE = CTA2 ? 4u : 2u;    // weight ring: 2 stages of one K block (two 32-k sub-blobs, 32 KB at N = 256)
-  constexpr uint32_t STAGE_BYTES = CTA2 ? 16384u : 32768u;
+  constexpr uint32_t NSTAGE = 2u;               // weight ring: 2 stages of one K block (two 32-k sub-blobs, 32 KB at N = 256)
+  constexpr uint32_t STAGE_BYTES = 32768u;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-  const bool leader = MC || rank == 0;      // MC: every CTA issues its own MMAs
 
   const long long n_tiles = (p.P + 127) / 128;
-  // work units: CTA2: "pair tiles" q (tiles 2q, 2q+1 for ranks 0,1); else single tiles
+  // work units: MC: "pair tiles" q (tiles 2q, 2q+1 for ranks 0,1); else single tiles
   const long long n_units = PAIR ? (n_tiles + 1) / 2 : n_tiles;
   const long long ncl = PAIR ? gridDim.x / 2 : gridDim.x, cid = PAIR ? blockIdx.x / 2 : blockIdx.x;
   auto unit_of = [&](int slot, long long it) { return (it * ncl + cid) * 2 + slot; };
@@ -261,12 +255,12 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
       mbar_init(b_pfull + 8 * i, 1);
     }
     for (uint32_t i = 0; i < 2; ++i) {
-      mbar_init(b_aready + 8 * i, CTA2 ? 2 * kEpiThreads : kEpiThreads);
+      mbar_init(b_aready + 8 * i, kEpiThreads);
       mbar_init(b_accready + 8 * i, 1);
     }
     fence_barrier_init();
   }
-  if (warp == 1) { if (CTA2) tmem_alloc2(s_tmem, 512); else tmem_alloc(s_tmem, 512); }
+  if (warp == 1) tmem_alloc(s_tmem, 512);
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();      // peer barriers are initialised before any remote arrive / multicast
@@ -281,23 +275,13 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
       for (long long it = 0; it < max_it; ++it) {
 #pragma unroll 1
         for (int s = 0; s < kFwdSteps; ++s) {
-          const uint32_t bytes = CTA2 ? fwd_blob_bytes(s) / 2 : fwd_blob_bytes(s);      // CTA2: this CTA's share of the N rows
-          const uint8_t* src = p.wpk + fwd_w_off(s) + (CTA2 ? rank * bytes : 0u);
+          const uint32_t bytes = fwd_blob_bytes(s);
+          const uint8_t* src = p.wpk + fwd_w_off(s);
           for (int slot = 0; slot < 2; ++slot) {
             if (unit_of(slot, it) >= n_units) continue;
             for (int kb = 0; kb < fwd_nkb(s); ++kb) {
               mbar_wait(b_wempty + 8 * stage, phase ^ 1);
               if (p.abl & 8) { mbar_arrive(b_wfull + 8 * stage); if (++stage == NSTAGE) { stage = 0; phase ^= 1; } continue; }
-              if (CTA2) {
-                // both CTAs' halves complete_tx on the LEADER's barrier (cta_group::2 tensor loads): no forwarding hop
-                if (rank == 0) mbar_expect_tx(b_wfull + 8 * stage, 2 * bytes);
-                const uint32_t lbar = (b_wfull + 8 * stage) & 0xFEFFFFFFu;
-                const int row0 = (int)((fwd_w_off(s) + (uint32_t)kb * fwd_blob_bytes(s) + rank * bytes) >> 7);
-                for (uint32_t i = 0; i < bytes; i += 8192u)
-                  tma_load_2d_pair(s_w + stage * STAGE_BYTES + i, &p.tmap_w, 0, row0 + (int)(i >> 7), lbar);
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                continue;
-              }
               mbar_expect_tx(b_wfull + 8 * stage, bytes);
               const uint32_t q4 = bytes >> 2;
               if (MC) {        // my half of the stage, delivered to both CTAs (the other half arrives from the peer)
@@ -319,19 +303,19 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
     }
   } else if (warp == 1) {
     uint32_t stage = 0, phase = 0, par_a[2] = {0, 0};
-    if (leader) {
+    {
       // ============================== MMA issuer ==============================
       long long pa = 0, pw = 0, pp = 0;
       const long long tstart = clock64();
       for (long long it = 0; it < max_it; ++it) {
 #pragma unroll 1
         for (int s = 0; s < kFwdSteps; ++s) {
-          const uint32_t idesc = umma_idesc(CTA2 ? 256 : 128, fwd_n(s), 0, 0);
+          const uint32_t idesc = umma_idesc(128, fwd_n(s), 0, 0);
           const int nkb = fwd_nkb(s);
           for (int slot = 0; slot < 2; ++slot) {
             if (unit_of(slot, it) >= n_units) continue;
             { const long long t0 = clock64();
-              if (CTA2) mbar_wait_cluster(b_aready + 8 * slot, par_a[slot]); else mbar_wait(b_aready + 8 * slot, par_a[slot]);
+              mbar_wait(b_aready + 8 * slot, par_a[slot]);
               pa += clock64() - t0; }
             par_a[slot] ^= 1;
             tc_fence_after();
@@ -365,8 +349,6 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
         long long* o = p.prof + (size_t)blockIdx.x * 8;
         o[0] = pa; o[1] = pw; o[2] = pp; o[3] = clock64() - tstart;
       }
-    } else {
-      // peer CTA of a pair: its tensor core is driven by the leader's cta_group::2 MMAs; nothing to issue here
     }
   } else {
     // ============================== epilogue groups ==============================
@@ -378,7 +360,6 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
     const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + (uint32_t)slot * 256u;
     const int grp_tid = threadIdx.x - (64 + slot * kEpiThreads);    // 0..255 inside the epilogue group
     const int bar_id = kBarEpi0 + slot;
-    const uint32_t a_ready_addr = CTA2 ? mapa_u32(b_aready + 8 * slot, 0) : 0u;   // the LEADER's barrier
     uint32_t par_acc = 0;
     long long pe_wait = 0, pe_body = 0, pe_pro = 0;
 
@@ -386,7 +367,7 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
       const long long unit = unit_of(slot, it);
       if (unit >= n_units) break;
       const long long tile = PAIR ? unit * 2 + rank : unit;
-      const bool tile_ok = tile < n_tiles;                  // CTA2: the last pair may have a ghost second tile
+      const bool tile_ok = tile < n_tiles;                  // MC: the last pair may have a ghost second tile
       const long long pt = tile * 128 + r;
       const bool valid = pt < p.P;
       const long long pc = valid ? pt : p.P - 1;            // clamp: padded rows compute finite garbage
@@ -408,7 +389,7 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
         emb_row_to_smem(aux_base + r * 128u, r, p.x_emb + pc * p.ld_x, 63, TRAIN, half * 4, half * 4 + 4, g_embx);
       }
       fence_proxy_async_smem();
-      if (CTA2) mbar_arrive_cluster(a_ready_addr); else mbar_arrive(b_aready + 8 * slot);
+      mbar_arrive(b_aready + 8 * slot);
       pe_pro += clock64() - t_p0;
 
       float sigma = 0.f;
@@ -451,7 +432,7 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
         tc_fence_before();
         pe_body += clock64() - t_e0;
         if (s < kFwdSteps - 1) {      // release the MMA warp first: it needs only every thread's own (fenced) stores, not the group barrier
-          if (CTA2) mbar_arrive_cluster(a_ready_addr); else mbar_arrive(b_aready + 8 * slot);
+          mbar_arrive(b_aready + 8 * slot);
         }
         if (s == kFwdSteps - 1) {
           named_bar_sync(bar_id, kEpiThreads);                  // scratch rows of the other column half are visible
@@ -472,7 +453,7 @@ mlp_fwd_chain_kernel(const __grid_constant__ FwdParams p) {
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();      // nobody exits while the partner may still signal its barriers / write its smem
-  if (warp == 1) { if (CTA2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -622,48 +603,18 @@ int nb_tc_pack(nb_handle_t h, const nb_mlp_desc* d, const float* params, void* p
 }
 
 // Tensor map over the packed forward blobs for the pair mode, encoded through the driver entry point (no libcuda link).
-static int make_weight_tmap(nb_handle_t h, CUtensorMap* tm, const void* packed) {
-  typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static encode_t enc = nullptr;
-  if (!enc) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    NB_CUDA(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-    if (q != cudaDriverEntryPointSuccess || !fn) { NB_SET_ERR(h, "cuTensorMapEncodeTiled unavailable"); return NB_ERR_CUDA; }
-    enc = (encode_t)fn;
-  }
-  const cuuint64_t dims[2] = {64, (cuuint64_t)(nb_tc_fwd_packed_bytes() / 128)};
-  const cuuint64_t strides[1] = {128};
-  const cuuint32_t box[2] = {64, 64};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(packed), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { NB_SET_ERR(h, "cuTensorMapEncodeTiled failed"); return NB_ERR_CUDA; }
-  return NB_OK;
-}
-
 static int launch_fwd(nb_handle_t h, FwdParams& fp, bool train, cudaStream_t st) {
   const bool dbg = fp.dbg != nullptr;
-  // cluster mode: 0 = independent CTAs, 1 = CTA pairs issuing cta_group::2 MMAs, 2 = independent MMAs + multicast weight ring
+  // cluster mode: 0 = independent CTAs, 2 = clusters of two CTAs sharing the weight stream by multicast (default)
   static int mode_env = -1;
   if (mode_env < 0) { const char* e = getenv("NB_TC_CLUSTER"); mode_env = e ? atoi(e) : 2; }
   const int mode = mode_env;
-  if (mode == 1) { NB_SET_ERR(h, "NB_TC_CLUSTER=1 (cta_group::2 MMAs) is not available with the sub-blob weight ring"); return NB_ERR_UNSUPPORTED; }
+  if (mode != 0 && mode != 2) { NB_SET_ERR(h, "NB_TC_CLUSTER must be 0 or 2"); return NB_ERR_INVALID; }
   const bool cta2 = mode != 0;      // launched as clusters of 2
-  if (mode == 1) {
-    static_assert(sizeof(CUtensorMap) <= sizeof(h->w_tmap), "tensor map does not fit the handle slot");
-    CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(h->w_tmap);
-    if (h->w_tmap_for != fp.wpk) { const int rc = make_weight_tmap(h, tm, fp.wpk); if (rc) return rc; h->w_tmap_for = fp.wpk; }
-    fp.tmap_w = *tm;
-  }
   typedef void (*kern_t)(const FwdParams);
   kern_t kern;
-  if (mode == 1) kern = dbg ? mlp_fwd_chain_kernel<false, true, true, false> : (train ? mlp_fwd_chain_kernel<true, false, true, false> : mlp_fwd_chain_kernel<false, false, true, false>);
-  else if (mode == 2) kern = dbg ? mlp_fwd_chain_kernel<false, true, false, true> : (train ? mlp_fwd_chain_kernel<true, false, false, true> : mlp_fwd_chain_kernel<false, false, false, true>);
-  else kern = dbg ? mlp_fwd_chain_kernel<false, true, false, false> : (train ? mlp_fwd_chain_kernel<true, false, false, false> : mlp_fwd_chain_kernel<false, false, false, false>);
+  if (mode == 2) kern = dbg ? mlp_fwd_chain_kernel<false, true, true> : (train ? mlp_fwd_chain_kernel<true, false, true> : mlp_fwd_chain_kernel<false, false, true>);
+  else kern = dbg ? mlp_fwd_chain_kernel<false, true, false> : (train ? mlp_fwd_chain_kernel<true, false, false> : mlp_fwd_chain_kernel<false, false, false>);
   const int ki = (dbg ? 2 : (train ? 1 : 0)) + 3 * mode;
   if (!h->fwd_attr_done[ki]) {
     NB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
@@ -715,7 +666,7 @@ static int launch_fwd(nb_handle_t h, FwdParams& fp, bool train, cudaStream_t st)
       if (host[b * 8 + 3] > tmax) tmax = host[b * 8 + 3];
     }
     fprintf(stderr, "nb_tc prof: MMA loop cycles per CTA min %lld max %lld (static round-robin tiles: the kernel ends with the slowest)\n", tmin, tmax);
-    fprintf(stderr, "nb_tc prof P=%lld train=%d cta2=%d: mma_wait_aready=%.0f mma_wait_wfull=%.0f mma_wait_peerfull=%.0f mma_total=%.0f "
+    fprintf(stderr, "nb_tc prof P=%lld train=%d clusters=%d: mma_wait_aready=%.0f mma_wait_wfull=%.0f mma_wait_peerfull=%.0f mma_total=%.0f "
             "epi_wait_acc=%.0f epi_body=%.0f epi_prologue=%.0f\n",
             fp.P, (int)train, (int)cta2, a[0] / n, a[1] / n, a[2] / n, a[3] / n, a[4] / n, a[5] / n, a[6] / n);
   }

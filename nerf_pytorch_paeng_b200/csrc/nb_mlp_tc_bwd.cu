@@ -10,13 +10,19 @@
 //        1..7: dh_{l-1} = (dh_l . W_l[:, skip cols]) * (h_{l-1} > 0)   for l = 7..1
 //  (2) wgrad -- dW_l = dY_l^T . X_l reduced over all points.  The stashed blobs ([128 points x 64 features] in the chunk-major
 //      layout of stash_off(): [point/64][feature/8][point%64][8 features]) are exactly SWIZZLE_NONE "MN-major" UMMA operands, so
-//      both A = dY_l and B = X_l are bulk-loaded (8 KB half blobs) and fed to tcgen05.mma without any transposition; the 256x256 fp32 accumulator of one weight matrix fills the
-//      512 TMEM columns.  The 11 (layer, input-block) jobs form one line of work cut into equal-traffic slices, one per
-//      CTA (wgrad is HBM-bound: 78 operand blobs per tile, see wg_segment); the folded feature + view layers are ONE job
-//      G = dg^T [h7 | PE(d)] (second accumulator region for the PE block; fold_grads_kernel maps G to dWf, dbf and dWd[:, :256])
-//      and the density head rides on that job's h7 operand; bias gradients are
-//      column sums of the dY tiles taken from shared memory by spare warps; results are added to the flat fp32
-//      gradient with red.global.add (v4 where the rows are 16-byte aligned).
+//      both A = dY_l and B = X_l are bulk-loaded (8 KB half blobs) and fed to tcgen05.mma without any transposition; the 256x256
+//      fp32 accumulator of one weight matrix fills the 512 TMEM columns.  The kernel is HBM-bound (78 operand blobs per tile, no
+//      reuse), so it is built around the byte stream:
+//        * 11 (layer, input-block) jobs; units of 64 points are claimed in chunks from per-job counters, every CTA starting on a
+//          home job chosen by byte share and moving on to the job with most bytes left (see the comment above mlp_wgrad_kernel);
+//        * a 216 KB operand ring cut into 3..6 stages by the job's unit size, so every job keeps ~200 KB in flight;
+//        * the folded feature + view layers are ONE job G = dg^T [h7 | PE(d)] (second accumulator region for the PE block;
+//          fold_grads_kernel maps G to dWf, dbf and dWd[:, :256]) and the density head rides on that job's h7 operand;
+//        * bias gradients: from the tensor cores where the B operand has a constant 1.0 column (the pad column of the PE blobs),
+//          else column sums of the staged dY tiles by the eight flush warps;
+//        * results are added to the flat fp32 gradient with red.global.add (v4 where the rows are 16-byte aligned).
+//      Measured on the fine pass of a 4096-ray step (7.85 GB): 1.37 ms with a static equal-byte split and a 3-stage ring for every
+//      job, 1.08-1.18 ms now = the 7.2 TB/s the same ring streams with no tensor work at all (scripts/wgrad_probe.cu).
 #include <stdlib.h>
 #include "nb_mlp_tc.h"
 #include "nb_tc_common.cuh"

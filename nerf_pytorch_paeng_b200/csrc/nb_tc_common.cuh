@@ -94,12 +94,6 @@ __device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst_smem, const void* sr
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
                ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
 }
-// 2-D tensor-map tile load issued by either CTA of a pair (cta_group::2): the bytes land in the ISSUING CTA's shared memory,
-// but complete_tx is signalled on `mbar`, which may be the LEADER's barrier (CTA-rank bit 24 of the address cleared)
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t mbar) {
-  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(mbar) : "memory");
-}
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
 }
@@ -129,15 +123,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// CTA-pair (cta_group::2) variants: allocation is executed by one warp in EACH CTA of the pair
-__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
 
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor, SWIZZLE_128B.  start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
@@ -180,27 +165,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// CTA-pair MMA (M = 256 over two SMs): issued by one thread of the LEADER CTA; A rows 0..127 / B rows 0..N/2-1 come from
-// the leader's shared memory, A rows 128..255 / B rows N/2..N-1 from the peer's, at the SAME shared-memory offsets;
-// each CTA's TMEM receives its own 128 rows x N columns.
-__device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 // single-CTA MMAs, but the arrive is multicast to the barrier at this offset in both CTAs of the cluster
 __device__ __forceinline__ void umma_commit_mcast(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
-// arrive on the mbarrier at this shared-memory offset in BOTH CTAs of the pair once the pair's MMAs have retired
-__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-
 // ---------------------------------------------------------------- bf16 packing
 // {lo, hi} -> bf16x2 word (lo in bits [0,16)), round-to-nearest-even, optional relu
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
