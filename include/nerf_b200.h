@@ -76,9 +76,10 @@ int nb_abi_version(void);
 /* device: CUDA ordinal.  flags: reserved, 0.  Fails with NB_ERR_CUDA if there is no GPU and
  * NB_ERR_UNSUPPORTED if the GPU is not compute capability 10.x.
  * Threading / streams: a handle is used by one host thread at a time.  All work is stream-ordered on the stream passed
- * to each call; the bf16 MLP entries stage their per-network constants (biases, head weights) in one __constant__
- * bank per device, so MLP calls for the same device must be issued on ONE stream at a time (other entries, and
- * handles on different devices, are independent). */
+ * to each call, and calls on different streams or handles are independent.  The bf16 MLP entries stage their per-network
+ * constants (biases, head weights) in a __constant__ bank bound to the calling stream (four banks per device, shared by
+ * the handles of that device): up to four streams run MLP kernels concurrently with no ordering between them; a further
+ * stream takes over the least recently used bank after a stream-side wait for that bank's previous owner. */
 int nb_create(nb_handle_t* out, int device, unsigned flags);
 int nb_destroy(nb_handle_t h);
 const char* nb_last_error(nb_handle_t h);
