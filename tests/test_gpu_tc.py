@@ -229,10 +229,13 @@ def emulate_backward(p, st, d_raw, P):
     return grads
 
 
-@pytest.mark.parametrize('n,s', [(3, 50), (5, 60), (300, 192)])   # (5,60): 3 tiles -> a ghost tile in the last CTA pair
+# (5,60): 3 tiles -> a ghost tile in the last CTA pair; the sizes step through the weight-gradient kernel's chunk sizes (1, 4, 8 and
+# 16 units per claim) and from fewer CTAs than jobs to every CTA visiting several jobs
+@pytest.mark.parametrize('n,s', [(3, 50), (5, 60), (300, 192), (1024, 192), (2800, 192)])
 def test_tc_backward_kernels(setup, n, s):
     """dgrad chain + wgrad against a numpy emulation of the same bf16 data flow driven by the kernel's own
-    stash (saved activations and ReLU masks): isolates the backward kernels from forward rounding."""
+    stash (saved activations and ReLU masks): isolates the backward kernels from forward rounding.  Also pins the pad columns of the
+    PE blobs to the constant 1.0 the tensor-core bias sums rely on."""
     from nerf_pytorch_paeng_b200._lib import NB_BF16
     eng, net, g = setup
     m = net.model_coarse
@@ -260,6 +263,7 @@ def test_tc_backward_kernels(setup, n, s):
     emb = orc.embed_points(rays, z)
     assert np.abs(st['embx'][:P, :63] - bf16(emb[:, :63])).max() <= 2e-2
     assert np.abs(st['embd'][:P, :27] - bf16(emb[:, 63:])).max() <= 2e-2
+    assert np.all(st['embx'][:P, 63] == 1.0) and np.all(st['embd'][:P, 27] == 1.0) and np.all(st['embd'][:P, 28:] == 0.0)
     for i in range(8):
         assert np.array_equal(st['mask'][i][:P], st[f'h{i}'][:P] > 0), i
     assert np.array_equal(st['mask'][8][:P, :128], st['g'][:P] > 0)
