@@ -339,7 +339,7 @@ constexpr int kWgThreads = 320;                         // warp0 producer, warp1
 constexpr int kWgMaxStages = 6;
 constexpr uint32_t kWgRingBytes = 216 * 1024;
 constexpr uint32_t kWgOffBar = kWgRingBytes;            // full[6] | empty[6] (+64) | done (+128) | tmem slot (+136) | free (+144)
-constexpr uint32_t kWgOffMeta = kWgOffBar + 192;        // [kWgMaxStages] x 8 B: what the stage holds (written by the producer, see WgMeta)
+constexpr uint32_t kWgOffMeta = kWgOffBar + 192;        // [kWgMaxStages] x 8 B: what the stage holds: {job | kWgFirst / kWgLast / kWgEnd, unit index} (written by the producer)
 constexpr uint32_t kWgOffSig = kWgOffBar + 256;         // [3][64 rows x 16 B] d_raw rows of the stage's points (density-head rider, <= 3 stages)
 constexpr uint32_t kWgSigStages = 3;
 constexpr uint32_t kWgSmemBytes = kWgOffSig + kWgSigStages * 1024 + 1024;
