@@ -144,3 +144,173 @@ def test_flat_adam_is_a_torch_optimizer_with_adam_state_dict():
                                                                                   min_lr=5e-5, warmup_steps=10000)
         assert abs(opt.param_groups[0]['lr'] - 5e-5) < 1e-12                                       # scheduler.py:48-52 init_lr
         assert cos.optimizer is opt
+
+
+def test_wgrad_claim_protocol_model():
+    """Model of the work distribution of mlp_wgrad_kernel (csrc/nb_mlp_tc_bwd.cu, producer thread): per-job chunk counters, home
+    job by byte share, early claim of the next chunk, move to the job with the most unclaimed bytes.  Under random interleavings of
+    the CTAs' atomic operations every unit of every job is processed exactly once, every CTA terminates, and a CTA flushes its
+    accumulator (ends a segment) exactly when it leaves a job."""
+    import random
+
+    def run(n_units, weights, grid, chunk, seed):
+        rnd = random.Random(seed)
+        n_jobs = len(weights)
+        n_chunks = -(-n_units // chunk)
+        counters = [0] * n_jobs
+        work_begin, total = [], 0
+        for w in weights:
+            work_begin.append(total)
+            total += w * n_units
+
+        def atomic_add(j):
+            v = counters[j]
+            counters[j] += 1
+            return v
+
+        def cta(b):
+            """generator: yields at every global-memory operation (the scheduler interleaves there); returns its segments"""
+            lo = total * b // grid
+            j = max(k for k in range(n_jobs) if work_begin[k] <= lo)
+            segments = []
+            while True:
+                yield
+                c = atomic_add(j)
+                while c >= n_chunks:
+                    yield
+                    left = [(n_chunks - counters[k]) * weights[k] for k in range(n_jobs)]      # the scan (plain loads)
+                    best = max(left)
+                    if best <= 0:
+                        return segments
+                    j = left.index(best)
+                    yield
+                    c = atomic_add(j)
+                seg = []
+                while c < n_chunks:
+                    yield
+                    cn = atomic_add(j)                    # next chunk of the same job, claimed before this one is streamed
+                    seg.extend((j, u) for u in range(c * chunk, min(c * chunk + chunk, n_units)))
+                    c = cn
+                segments.append(seg)                      # `last` flag on the final unit: accumulator flushed here
+
+        gens = {b: cta(b) for b in range(grid)}
+        done = {}
+        steps = 0
+        while gens:
+            b = rnd.choice(list(gens))
+            try:
+                next(gens[b])
+            except StopIteration as e:
+                done[b] = e.value
+                del gens[b]
+            steps += 1
+            assert steps < 10_000_000, 'claim protocol does not terminate'
+        seen = {}
+        for b, segs in done.items():
+            for seg in segs:
+                assert seg and len({j for j, _ in seg}) == 1          # a segment is one job
+                for ju in seg:
+                    assert ju not in seen, ('claimed twice', ju)
+                    seen[ju] = b
+        assert len(seen) == n_jobs * n_units
+        assert max(counters) <= n_chunks + 2 * grid + n_jobs          # over-claims stay bounded (uint32 counters)
+        return done
+
+    weights = [5, 8, 8, 8, 8, 5, 8, 8, 8, 7, 4]                        # operand blobs per unit of the 11 jobs
+    for n_units, grid, chunk, seed in [(6, 6, 1, 0), (4, 4, 1, 1), (97, 13, 4, 2), (900, 148, 4, 3), (4096, 148, 8, 4), (12288, 148, 16, 5),
+                                       (2, 2, 1, 6), (33, 148, 1, 7)]:
+        done = run(n_units, weights, min(grid, n_units), chunk, seed)
+        assert len(done) == min(grid, n_units)
+
+
+def test_wgrad_ring_parity_model():
+    """Model of mlp_wgrad_kernel's operand ring: up to six stage barriers, each with its OWN phase parity kept in a bit mask by the
+    producer (initially all ones: the first wait on a fresh barrier passes) and by every consumer (initially zero), because the number
+    of stages in use changes from segment to segment; the ring is drained between segments and stage numbering restarts at 0.  Under
+    random scheduling: the consumer reads exactly the sequence the producer wrote, no stage is refilled before it was released, and
+    nobody deadlocks."""
+    import random
+
+    class Bar:                                   # mbarrier with a fixed arrival count; try_wait.parity semantics
+        def __init__(self, count):
+            self.count, self.pending, self.phase = count, count, 0
+
+        def arrive(self):
+            self.pending -= 1
+            if self.pending == 0:
+                self.pending, self.phase = self.count, self.phase + 1
+
+        def done(self, parity):                  # "the phase with this parity has completed"
+            return (self.phase & 1) != parity
+
+    def run(segments, seed):
+        rnd = random.Random(seed)
+        full = [Bar(1) for _ in range(6)]
+        empty = [Bar(2) for _ in range(6)]       # two consumers (MMA commit + the column-sum warps, as one party each)
+        slots = [None] * 6
+        written, read = [], [[], []]
+        END = ('end',)
+
+        def producer():
+            pmask, any_seg = 0x3F, False
+            for ns, items in segments:
+                if any_seg:
+                    for i in range(6):           # drain
+                        while not empty[i].done((pmask >> i) & 1):
+                            yield
+                any_seg = True
+                stage = 0
+                for k, it in enumerate(items):
+                    while not empty[stage].done((pmask >> stage) & 1):
+                        yield
+                    pmask ^= 1 << stage
+                    assert slots[stage] is None, 'stage refilled before it was released'
+                    slots[stage] = (it, ns, k == len(items) - 1)
+                    written.append(it)
+                    full[stage].arrive()
+                    yield
+                    stage = (stage + 1) % ns
+            if any_seg:
+                for i in range(6):
+                    while not empty[i].done((pmask >> i) & 1):
+                        yield
+            slots[0] = (END, 1, True)
+            full[0].arrive()
+
+        def consumer(who):
+            cmask, stage = 0, 0
+            while True:
+                while not full[stage].done((cmask >> stage) & 1):
+                    yield
+                cmask ^= 1 << stage
+                it, ns, last = slots[stage]
+                if it is END:
+                    return
+                read[who].append(it)
+                yield
+                empty[stage].arrive()
+                if empty[stage].pending == empty[stage].count:      # both consumers released it
+                    slots[stage] = None
+                stage = 0 if last else (stage + 1) % ns
+
+        gens = [producer(), consumer(0), consumer(1)]
+        alive = list(range(3))
+        steps = 0
+        while alive:
+            i = rnd.choice(alive)
+            try:
+                next(gens[i])
+            except StopIteration:
+                alive.remove(i)
+            steps += 1
+            assert steps < 2_000_000, 'ring protocol deadlocks'
+        assert read[0] == written and read[1] == written
+
+    rs = random.Random(0)
+    for seed in range(20):
+        segs, n = [], 0
+        for _ in range(rs.randint(0, 4)):
+            ns, cnt = rs.choice([3, 3, 5, 6]), rs.randint(1, 40)
+            segs.append((ns, list(range(n, n + cnt))))
+            n += cnt
+        run(segs, seed)
