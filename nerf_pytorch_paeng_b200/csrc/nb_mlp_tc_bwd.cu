@@ -847,7 +847,7 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
     add(w8 + W.off_draw, 2, 0, 2, stash + S.off_g, 2, 0, 2, grad + L.wc, 128, 0, 3, 128, grad + L.bc);          // dWc, dbc
     wp.n_jobs = nj;
     wp.n_points = P;
-    // every CTA streams an equal slice of the concatenated job list (wg_segment)
+    // the byte-weighted line of work (work_begin / total_work) only picks every CTA's HOME job; units are claimed dynamically
     long long work = 0;
     for (int j = 0; j < nj; ++j) {
       wp.job[j].weight = weight[j]; wp.job[j].work_begin = work; work += (long long)weight[j] * n_tiles * 2;
