@@ -318,6 +318,7 @@ struct WgradJob {
   float* sig_bias;
   int weight;            // operand blobs streamed per unit (64 points)
   int n_stages;          // ring stages for this job: min(kWgMaxStages, kWgRingBytes / stage bytes)
+  int share;             // CTAs expected on this job (grid x its share of the bytes, >= 1): sizes the shrinking claims at the job's end
   long long work_begin;  // sum of weight * n_units over the preceding jobs
 };
 struct WgradParams {
@@ -325,8 +326,8 @@ struct WgradParams {
   int n_jobs;
   long long n_tiles, n_points, total_work;
   int abl;
-  int chunk_units;             // units (64 points) per dynamically claimed chunk
-  unsigned int* counters;      // [kMaxJobs] next unclaimed chunk of every job (zeroed before the launch)
+  int chunk_units;             // most units (64 points) per dynamically claimed chunk
+  unsigned int* counters;      // [kMaxJobs] next unclaimed unit of every job (zeroed before the launch)
   unsigned long long* prof;    // optional [grid][4] ns time stamps (NB_TC_PROF diagnostic)
 };
 
@@ -347,7 +348,7 @@ static_assert(kWgSmemBytes <= 232448, "wgrad ring exceeds the 227 KB of shared m
 // stage descriptor word 0: job | flags
 constexpr uint32_t kWgFirst = 1u << 8, kWgLast = 1u << 9, kWgEnd = 1u << 10;
 
-// Work distribution.  A job's units are claimed in chunks of `chunk_units` from a per-job atomic counter.  Every CTA starts on
+// Work distribution.  A job's units are claimed in chunks of at most `chunk_units` (fewer towards the job's end) from a per-job atomic counter.  Every CTA starts on
 // its HOME job -- the one that holds the start of its share of the byte-weighted line of work, so jobs get CTAs in proportion to
 // their traffic -- and keeps claiming there; when the job is exhausted it flushes its accumulator and moves to the job with the
 // most unclaimed bytes left.  (A static equal-byte split finished between 0.92 and 1.15 ms per CTA on the fine pass: SMs differ
@@ -393,25 +394,35 @@ mlp_wgrad_kernel(const WgradParams p) {
       // job's stage slots have another size and would overlap slots the MMAs may still be reading.
       uint32_t pmask = (1u << kWgMaxStages) - 1u;
       const long long C = p.chunk_units;
-      const long long n_chunks = (n_units + C - 1) / C;
+      // Claim [ua, ub) of job jj: up to C units, fewer towards the end of the job (half of an even share of what `seen` -- the last
+      // counter value this thread saw -- leaves), so that the CTAs of a job run out of work together instead of one chunk apart.
+      auto claim = [&](int jj, long long seen, long long& ua, long long& ub) -> bool {
+        const long long share = p.job[jj].share;
+        long long k = (n_units - seen + 2 * share - 1) / (2 * share);
+        k = k > C ? C : (k < 1 ? 1 : k);
+        ua = (long long)atomicAdd(p.counters + jj, (unsigned int)k);
+        ub = ua + k < n_units ? ua + k : n_units;
+        return ua < n_units;
+      };
       int j = wg_home_job(p, p.total_work * (long long)blockIdx.x / (long long)gridDim.x);
       bool any = false;
       long long units_done = 0;
       while (true) {
         // ---- claim the first chunk of a segment: the home job first, afterwards whichever job has the most bytes unclaimed
-        long long c = (long long)atomicAdd(p.counters + j, 1u);
-        while (c >= n_chunks) {
-          long long best = 0; int bj = -1;
+        long long ua, ub;
+        bool got = claim(j, (long long)*reinterpret_cast<volatile unsigned int*>(p.counters + j), ua, ub);
+        while (!got) {
+          long long best = 0, best_taken = 0; int bj = -1;
           for (int k = 0; k < p.n_jobs; ++k) {
             const long long taken = (long long)*reinterpret_cast<volatile unsigned int*>(p.counters + k);
-            const long long left = (n_chunks - taken) * p.job[k].weight;
-            if (left > best) { best = left; bj = k; }
+            const long long left = (n_units - taken) * p.job[k].weight;
+            if (left > best) { best = left; bj = k; best_taken = taken; }
           }
           if (bj < 0) break;
           j = bj;
-          c = (long long)atomicAdd(p.counters + j, 1u);
+          got = claim(j, best_taken, ua, ub);
         }
-        if (c >= n_chunks) break;
+        if (!got) break;
         const WgradJob& J = p.job[j];
         const uint32_t stage_bytes = (uint32_t)(J.m_blk + J.n_blk + J.n2_blk) * 8192u;
         const uint32_t ns = (uint32_t)J.n_stages;
@@ -420,9 +431,9 @@ mlp_wgrad_kernel(const WgradParams p) {
         any = true;
         uint32_t stage = 0;
         bool first = true;
-        while (c < n_chunks) {
-          const long long cn = (long long)atomicAdd(p.counters + j, 1u);      // next chunk, claimed early: its latency hides behind this chunk
-          const long long ua = c * C, ub = (ua + C < n_units) ? ua + C : n_units;
+        while (got) {
+          long long na, nb;
+          const bool more = claim(j, ub, na, nb);      // next chunk, claimed early: its latency hides behind this chunk
           for (long long u = ua; u < ub; ++u) {
             const long long tile = u >> 1;
             const long long tile_a = (p.abl & 64) ? (tile & 63) : tile;      // experiments: operands from an L2-resident window
@@ -430,7 +441,7 @@ mlp_wgrad_kernel(const WgradParams p) {
             const uint32_t half = (uint32_t)(u & 1) * 8192u;
             mbar_wait(b_empty + 8 * stage, (pmask >> stage) & 1u);
             pmask ^= 1u << stage;
-            const uint32_t flags = (uint32_t)j | (first ? kWgFirst : 0u) | ((u == ub - 1 && cn >= n_chunks) ? kWgLast : 0u);
+            const uint32_t flags = (uint32_t)j | (first ? kWgFirst : 0u) | ((u == ub - 1 && !more) ? kWgLast : 0u);
             asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(s_meta + 8u * stage), "r"(flags), "r"((uint32_t)u) : "memory");
             first = false;
             long long rows = J.sig_draw ? p.n_points - u * 64 : 0;           // density-head rider: the unit's d_raw rows ride along
@@ -449,7 +460,7 @@ mlp_wgrad_kernel(const WgradParams p) {
             if (++stage == ns) stage = 0;
             ++units_done;
           }
-          c = cn;
+          got = more; ua = na; ub = nb;
         }
       }
       // ---- end of work: an empty stage that only carries the flag (stage 0 of a drained ring)
@@ -862,6 +873,14 @@ int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, con
       wp.chunk_units = per_cta >= 512 ? 16 : (per_cta >= 128 ? 8 : (per_cta >= 16 ? 4 : 1));
     }
     wp.counters = reinterpret_cast<unsigned int*>(fold_g + kFoldFloats);          // zeroed with the fold scratch above
+    {
+      int grid_n = h->sm_count;
+      if ((long long)grid_n > n_tiles * 2) grid_n = (int)(n_tiles * 2);
+      for (int j = 0; j < nj; ++j) {
+        const long long sh = (long long)grid_n * weight[j] * n_tiles * 2 / (work > 0 ? work : 1);
+        wp.job[j].share = sh < 1 ? 1 : (int)sh;
+      }
+    }
     int begin = h->sm_count;
     if ((long long)begin > n_tiles * 2) begin = (int)(n_tiles * 2);
     static unsigned long long* prof_dev = nullptr;

@@ -147,26 +147,29 @@ def test_flat_adam_is_a_torch_optimizer_with_adam_state_dict():
 
 
 def test_wgrad_claim_protocol_model():
-    """Model of the work distribution of mlp_wgrad_kernel (csrc/nb_mlp_tc_bwd.cu, producer thread): per-job chunk counters, home
-    job by byte share, early claim of the next chunk, move to the job with the most unclaimed bytes.  Under random interleavings of
-    the CTAs' atomic operations every unit of every job is processed exactly once, every CTA terminates, and a CTA flushes its
-    accumulator (ends a segment) exactly when it leaves a job."""
+    """Model of the work distribution of mlp_wgrad_kernel (csrc/nb_mlp_tc_bwd.cu, producer thread): per-job unit counters, home
+    job by byte share, claims of up to `chunk` units that shrink towards the end of a job, early claim of the next chunk, move to
+    the job with the most unclaimed bytes.  Under random interleavings of the CTAs' atomic operations every unit of every job is
+    processed exactly once, every CTA terminates, and a CTA flushes its accumulator (ends a segment) exactly when it leaves a job."""
     import random
 
     def run(n_units, weights, grid, chunk, seed):
         rnd = random.Random(seed)
         n_jobs = len(weights)
-        n_chunks = -(-n_units // chunk)
         counters = [0] * n_jobs
         work_begin, total = [], 0
         for w in weights:
             work_begin.append(total)
             total += w * n_units
+        share = [max(1, grid * w * n_units // total) for w in weights]
+        sizes = []
 
-        def atomic_add(j):
-            v = counters[j]
-            counters[j] += 1
-            return v
+        def claim(j, seen):
+            k = max(1, min(chunk, -(-(n_units - seen) // (2 * share[j]))))
+            ua = counters[j]
+            counters[j] += k
+            sizes.append(k)
+            return ua < n_units, ua, min(ua + k, n_units)
 
         def cta(b):
             """generator: yields at every global-memory operation (the scheduler interleaves there); returns its segments"""
@@ -175,22 +178,25 @@ def test_wgrad_claim_protocol_model():
             segments = []
             while True:
                 yield
-                c = atomic_add(j)
-                while c >= n_chunks:
+                seen = counters[j]
+                yield
+                got, ua, ub = claim(j, seen)
+                while not got:
                     yield
-                    left = [(n_chunks - counters[k]) * weights[k] for k in range(n_jobs)]      # the scan (plain loads)
+                    left = [(n_units - counters[k]) * weights[k] for k in range(n_jobs)]      # the scan (plain loads)
                     best = max(left)
                     if best <= 0:
                         return segments
                     j = left.index(best)
+                    seen = counters[j]
                     yield
-                    c = atomic_add(j)
+                    got, ua, ub = claim(j, seen)
                 seg = []
-                while c < n_chunks:
+                while got:
                     yield
-                    cn = atomic_add(j)                    # next chunk of the same job, claimed before this one is streamed
-                    seg.extend((j, u) for u in range(c * chunk, min(c * chunk + chunk, n_units)))
-                    c = cn
+                    more, na, nb = claim(j, ub)           # next chunk of the same job, claimed before this one is streamed
+                    seg.extend((j, u) for u in range(ua, ub))
+                    got, ua, ub = more, na, nb
                 segments.append(seg)                      # `last` flag on the final unit: accumulator flushed here
 
         gens = {b: cta(b) for b in range(grid)}
@@ -205,15 +211,16 @@ def test_wgrad_claim_protocol_model():
                 del gens[b]
             steps += 1
             assert steps < 10_000_000, 'claim protocol does not terminate'
-        seen = {}
+        seen_units = {}
         for b, segs in done.items():
             for seg in segs:
                 assert seg and len({j for j, _ in seg}) == 1          # a segment is one job
                 for ju in seg:
-                    assert ju not in seen, ('claimed twice', ju)
-                    seen[ju] = b
-        assert len(seen) == n_jobs * n_units
-        assert max(counters) <= n_chunks + 2 * grid + n_jobs          # over-claims stay bounded (uint32 counters)
+                    assert ju not in seen_units, ('claimed twice', ju)
+                    seen_units[ju] = b
+        assert len(seen_units) == n_jobs * n_units
+        assert max(counters) <= n_units + chunk * (2 * grid + n_jobs)          # over-claims stay bounded (uint32 counters)
+        assert max(sizes) <= chunk and min(sizes) >= 1
         return done
 
     weights = [5, 8, 8, 8, 8, 5, 8, 8, 8, 7, 4]                        # operand blobs per unit of the 11 jobs
