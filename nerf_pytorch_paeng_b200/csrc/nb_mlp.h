@@ -35,3 +35,8 @@ int nb_tc_forward(nb_handle_t h, const nb_mlp_desc* d, const float* params, cons
 int nb_tc_backward(nb_handle_t h, const nb_mlp_desc* d, const float* params, const void* packed, int64_t P,
                    const void* act_save, const float* d_raw, float* grad, int accumulate, void* ws, size_t ws_bytes,
                    cudaStream_t st, int stages = 3);
+
+// fused compositing + MSE gradient + compositing backward of the training drivers (nb_composite.cu); NB_ERR_UNSUPPORTED for S > 192
+int nb_composite_train(nb_handle_t h, int64_t N, int32_t S, const float* raw, const float* z, const float* rays_d, const float* target,
+                       float scale, float loss_scale, float* rgb, float* disp, float* weights, float* d_raw, float* loss_out,
+                       cudaStream_t st);

@@ -2,6 +2,7 @@
 // C-ABI call each.  Pure host-side sequencing of the library's own entry points on the caller's stream --
 // no allocation, no synchronisation; every intermediate lives in the caller's workspace.
 #include "nb_common.cuh"
+#include "nb_mlp.h"
 
 namespace {
 
@@ -102,6 +103,16 @@ int run_net(nb_handle_t h, const nb_mlp_desc* d, const nb_render_cfg* c, const P
     NB_LAUNCHED(h);
   }
   float* rgb = rgb_out ? rgb_out : p.rgb_tmp;
+  if (train) {      // compositing + loss gradient + compositing backward in one pass over raw (S <= 192), else stage by stage below
+    if (target_ready) NB_CUDA(h, cudaStreamWaitEvent(st, (cudaEvent_t)target_ready, 0));
+    const float scale = (float)(2.0 / (3.0 * n_global)), lscale = (float)(1.0 / (3.0 * n_global));
+    rc = nb_composite_train(h, N, S, p.raw, z, p.rays_d, target, scale, lscale, rgb, disp_out ? disp_out : p.disp_tmp, fine ? nullptr : w,
+                            p.d_raw, loss ? loss + (fine ? 1 : 0) : nullptr, st);
+    if (rc == NB_OK)
+      return nb_mlp_backward(h, d, params, packed, N * S, p.act, p.d_raw, grad, accumulate, c->precision, p.mlp_ws, p.mlp_ws_bytes, st);
+    if (rc != NB_ERR_UNSUPPORTED) return rc;
+    target_ready = nullptr;      // already waited for
+  }
   // the fine pass of render_rays drops weights/depth/acc (nerf_process.py:211-216); the coarse weights feed sample_pdf
   if ((rc = nb_composite_forward(h, N, S, p.raw, z, p.rays_d, rgb, disp_out ? disp_out : p.disp_tmp, nullptr, fine ? nullptr : w,
                                  nullptr, st))) return rc;
